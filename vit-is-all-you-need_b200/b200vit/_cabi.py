@@ -1,0 +1,88 @@
+"""ctypes binding of libb200vit.so (the C ABI in include/b200vit.h).
+
+There is deliberately no fallback: if the shared library is missing or the device is not sm_100,
+every op raises.  Tensors are passed as raw device pointers on torch's *current* stream.
+"""
+import ctypes
+import os
+import re
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200vit.so")
+HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "b200vit.h")
+
+_lib = None
+_lock = threading.Lock()
+_inited_devices = set()
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+
+
+class B200VitError(RuntimeError):
+    pass
+
+
+def declared_symbols(header_path: str = HEADER_PATH):
+    """Names of every function include/b200vit.h declares (used by the export test)."""
+    text = open(header_path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200vit_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """Loads the library once; raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise B200VitError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+                " There is no CPU / PyTorch fallback for the b200vit hot path.")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.b200vit_last_error.restype = ctypes.c_char_p
+        _lib = lib
+    return _lib
+
+
+def ensure_device(device_index: int):
+    lib = load()
+    if device_index not in _inited_devices:
+        rc = lib.b200vit_init(c_int(device_index))
+        if rc != 0:
+            raise B200VitError(lib.b200vit_last_error().decode())
+        _inited_devices.add(device_index)
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise B200VitError(f"libb200vit: {load().b200vit_last_error().decode()} (rc={rc})")
+
+
+def ptr(t):
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def lib_for(t: torch.Tensor):
+    if not t.is_cuda:
+        raise B200VitError("b200vit ops need CUDA tensors on a B200 (sm_100a); there is no CPU fallback")
+    return ensure_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def call(name: str, *args):
+    """Calls lib.<name>(*args) and raises on a non-zero return code."""
+    fn = getattr(load(), name)
+    check(fn(*args))

@@ -1,0 +1,173 @@
+// Host launchers + C ABI for the tcgen05 GEMM family (see gemm_tcgen05.cuh for the kernel).
+#include "../../include/b200vit.h"
+#include "gemm_tcgen05.cuh"
+
+namespace b200 {
+
+// Pick the K-split that minimises (waves x k-blocks per work item) on a persistent grid.
+static void plan_splits(GemmShape& s, bool allow_split) {
+  const int tiles = s.tiles_m * s.tiles_n;
+  const int sms = num_sms();
+  int best_splits = 1;
+  if (allow_split && tiles < sms) {
+    double best_cost = 1e30;
+    const int max_splits = s.kb_total < 64 ? s.kb_total : 64;
+    for (int sp = 1; sp <= max_splits; ++sp) {
+      const int kb_per = (s.kb_total + sp - 1) / sp;
+      const int eff = (s.kb_total + kb_per - 1) / kb_per;  // non-empty splits
+      if (eff != sp) continue;
+      const int waves = (tiles * sp + sms - 1) / sms;
+      const double cost = (double)waves * (kb_per + 8.0);  // +8: prologue/epilogue per work item
+      if (cost < best_cost) { best_cost = cost; best_splits = sp; }
+    }
+  }
+  s.splits = best_splits;
+  s.kb_per = (s.kb_total + best_splits - 1) / best_splits;
+  s.total_work = tiles * s.splits;
+}
+
+template <bool A_MN, bool B_MN, int BN, int KIND>
+static int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                  const EpiParams& ep, bool allow_split, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  GemmShape s;
+  s.M = M; s.N = N; s.K = K;
+  s.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  s.tiles_n = (N + BN - 1) / BN;
+  s.kb_total = (K + GEMM_BK - 1) / GEMM_BK;
+  s.mn_lbo = g_debug[0] ? g_debug[0] : 8192;
+  s.mn_sbo = g_debug[1] ? g_debug[1] : 1024;
+  s.mn_kadv = g_debug[2] ? g_debug[2] : 2048;
+  plan_splits(s, allow_split);
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (A_MN) rc = make_tmap_2d_bf16(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 64);
+  else      rc = make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM, 64);
+  if (rc != OK) return rc;
+  if (B_MN) rc = make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 64);
+  else      rc = make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, 64);
+  if (rc != OK) return rc;
+
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, KIND>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  Epilogue<KIND> epi;
+  epi.p = ep;
+  int grid = s.total_work < num_sms() ? s.total_work : num_sms();
+  if (g_debug[3] > 0 && grid > g_debug[3]) grid = g_debug[3];
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, s, epi);
+  B200_CUDA(cudaGetLastError());
+  return OK;
+}
+
+template <bool A_MN, bool B_MN, int KIND>
+static int launch_bn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                     const EpiParams& ep, bool allow_split, cudaStream_t st) {
+  // 128x256 tiles when N fills them; 128x128 otherwise (less padding waste for narrow outputs).
+  const bool wide = (g_debug[4] == 256) || (g_debug[4] != 128 && (N % 256 == 0 || N >= 1024));
+  if (wide) return launch<A_MN, B_MN, 256, KIND>(A, lda, B, ldb, M, N, K, ep, allow_split, st);
+  return launch<A_MN, B_MN, 128, KIND>(A, lda, B, ldb, M, N, K, ep, allow_split, st);
+}
+
+static int check_common(const void* a, const void* b, const void* c, int M, int N, int K) {
+  B200_REQUIRE(a && b && c, "gemm: null pointer");
+  B200_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: non-positive dimension M=%d N=%d K=%d", M, N, K);
+  B200_REQUIRE(N % 8 == 0 && K % 8 == 0, "gemm: N=%d and K=%d must be multiples of 8", N, K);
+  return OK;
+}
+
+static EpiParams make_ep(void* out, long long ldo) {
+  EpiParams ep;
+  ep.out = out; ep.ldo = ldo; ep.out2 = nullptr; ep.ldo2 = 0; ep.bias = nullptr;
+  ep.aux = nullptr; ep.ldaux = 0; ep.pos = nullptr; ep.P = 1; ep.T = 1; ep.extra = 0;
+  return ep;
+}
+
+// used by patchify.cu
+int gemm_patch_epilogue(const void* xcol, const void* w, const float* bias, const float* pos,
+                        float* out, int rows, int N, int K, int P, int T, int extra,
+                        cudaStream_t st) {
+  EpiParams ep = make_ep(out, N);
+  ep.bias = bias; ep.pos = pos; ep.ldaux = N; ep.P = P; ep.T = T; ep.extra = extra;
+  return launch_bn<false, false, EPI_PATCH_F32>(xcol, K, w, K, rows, N, K, ep, false, st);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200vit_gemm_bias(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
+                      void* stream) {
+  int rc = check_common(x, w, y, M, N, K);
+  if (rc) return rc;
+  EpiParams ep = make_ep(y, N);
+  ep.bias = bias;
+  return launch_bn<false, false, EPI_BF16>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
+}
+
+int b200vit_gemm_bias_gelu(const void* x, const void* w, const float* bias, void* g, void* u, int M,
+                           int N, int K, void* stream) {
+  int rc = check_common(x, w, g, M, N, K);
+  if (rc) return rc;
+  EpiParams ep = make_ep(g, N);
+  ep.bias = bias; ep.out2 = u; ep.ldo2 = N;
+  return launch_bn<false, false, EPI_GELU_BF16>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
+}
+
+int b200vit_gemm_bias_residual(const void* x, const void* w, const float* bias, const float* resid,
+                               float* out, int M, int N, int K, void* stream) {
+  int rc = check_common(x, w, out, M, N, K);
+  if (rc) return rc;
+  B200_REQUIRE(resid != nullptr, "gemm_bias_residual: resid is null");
+  EpiParams ep = make_ep(out, N);
+  ep.bias = bias; ep.aux = resid; ep.ldaux = N;
+  return launch_bn<false, false, EPI_RESID_F32>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
+}
+
+int b200vit_gemm_bias_f32(const void* x, const void* w, const float* bias, float* out, int M, int N,
+                          int K, void* stream) {
+  int rc = check_common(x, w, out, M, N, K);
+  if (rc) return rc;
+  EpiParams ep = make_ep(out, N);
+  ep.bias = bias;
+  return launch_bn<false, false, EPI_F32>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
+}
+
+// dx[M,K] = dy[M,N] w[N,K]: contraction over N; output columns = K.
+int b200vit_gemm_dgrad(const void* dy, const void* w, void* dx, int M, int N, int K, void* stream) {
+  int rc = check_common(dy, w, dx, M, N, K);
+  if (rc) return rc;
+  EpiParams ep = make_ep(dx, K);
+  return launch_bn<false, true, EPI_BF16>(dy, N, w, K, M, /*N_out=*/K, /*K_contract=*/N, ep, false,
+                                          (cudaStream_t)stream);
+}
+
+int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* u, void* dx, int M, int N,
+                             int K, void* stream) {
+  int rc = check_common(dy, w, dx, M, N, K);
+  if (rc) return rc;
+  B200_REQUIRE(u != nullptr, "gemm_dgrad_dgelu: u is null");
+  EpiParams ep = make_ep(dx, K);
+  ep.aux = u; ep.ldaux = K;
+  return launch_bn<false, true, EPI_DGELU_BF16>(dy, N, w, K, M, K, N, ep, false, (cudaStream_t)stream);
+}
+
+// dw[N,K] = dy[M,N]^T x[M,K]: output rows = N, output cols = K, contraction over M (split-K).
+int b200vit_gemm_wgrad(const void* dy, const void* x, float* dw, int M, int N, int K, int accumulate,
+                       void* stream) {
+  int rc = check_common(dy, x, dw, M, N, K);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  EpiParams ep = make_ep(dw, K);
+  if (!accumulate) B200_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+  return launch_bn<true, true, EPI_ATOMIC_F32>(dy, N, x, K, /*M_out=*/N, /*N_out=*/K,
+                                               /*K_contract=*/M, ep, true, st);
+}
+
+}  // extern "C"

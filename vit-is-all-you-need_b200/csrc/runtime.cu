@@ -1,0 +1,131 @@
+// Host runtime shared by all entry points: error strings, device checks, TMA tensor-map encoding.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/b200vit.h"
+#include "common.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+int g_debug[16] = {0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return OK;
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return ERR_CUDA;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int load_encode() {
+  if (g_encode != nullptr) return OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return ERR_CUDA;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return OK;
+}
+
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  int rc = load_encode();
+  if (rc != OK) return rc;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i];
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("TMA base pointer %p is not 16-byte aligned", base);
+    return ERR_ARG;
+  }
+  for (int i = 1; i < rank; ++i) {
+    if (strides_bytes[i] % 16 != 0) {
+      set_error("TMA stride %llu (dim %d) is not a multiple of 16 bytes",
+                (unsigned long long)strides_bytes[i], i);
+      return ERR_ARG;
+    }
+  }
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                        const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0],
+              rank > 1 ? box[1] : 0);
+    return ERR_CUDA;
+  }
+  return OK;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows, uint32_t box_cols) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[2] = {2, ld * 2};
+  const uint32_t box[2] = {box_cols, box_rows};
+  return make_tmap_nd_bf16(out, base, 2, dims, strides, box, true);
+}
+
+}  // namespace b200
+
+extern "C" {
+
+const char* b200vit_last_error(void) { return b200::g_err; }
+
+int b200vit_version(void) { return B200VIT_VERSION; }
+
+int b200vit_init(int device) {
+  cudaDeviceProp prop;
+  B200_CUDA(cudaSetDevice(device));
+  B200_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    b200::set_error("device %d is sm_%d%d; libb200vit only contains sm_100a code (no fallback)", device,
+                    prop.major, prop.minor);
+    return b200::ERR_DEVICE;
+  }
+  b200::g_num_sms = prop.multiProcessorCount;
+  return b200::load_encode();
+}
+
+int b200vit_debug_set(int key, int value) {
+  if (key < 0 || key >= 16) return b200::ERR_ARG;
+  b200::g_debug[key] = value;
+  return b200::OK;
+}
+
+}  // extern "C"
