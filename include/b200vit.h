@@ -53,6 +53,57 @@ int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* u, void*
 int b200vit_gemm_wgrad(const void* dy, const void* x, float* dw, int M, int N, int K, int accumulate,
                        void* stream);
 
+/* ---- fused flash attention, head_dim 64 ----------------------------------------------------------------
+ * qkv: [B, N, 3, H, 64] bf16 == the row-major output of the QKV Linear, "(qkv h d)" of transformer.py:27;
+ * o: [B, N, H*64] bf16 == "b h n d -> b n (h d)" of transformer.py:29; lse: [B, H, N] fp32 (may be NULL).
+ * Replaces F.scaled_dot_product_attention at transformer.py:28 (causal = additive -inf mask of
+ * transformer.py:22-25) and the SDPA inside nn.MultiheadAttention (blocks.py:60).  dropout_p must be 0. */
+int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int causal, void* stream);
+size_t b200vit_flash_attn_bwd_workspace_size(int B, int N, int H);
+/* dqkv: [B, N, 3, H, 64] bf16 gradient of qkv given d_o [B, N, H*64] bf16 */
+int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B,
+                           int N, int H, int causal, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- LayerNorm on the fp32 residual stream (F.layer_norm transformer.py:43-44; nn.LayerNorm blocks.py:43,48)
+ * fwd: v = x (+ add_bf16) ; x_out = v (optional) ; y = LN(v) * gamma + beta -> bf16 and/or fp32 ; saves mean, rstd
+ * bwd: dx = dres (optional) + LN'(dy) ; optional bf16 copy ; dgamma / dbeta (both or neither)               */
+int b200vit_layernorm_fwd(const float* x, const void* add_bf16, float* x_out, const float* gamma, const float* beta,
+                          void* y_bf16, float* y_f32, float* mean, float* rstd, int M, int d, float eps, void* stream);
+int b200vit_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean,
+                          const float* rstd, const float* gamma, const float* dres, float* dx, void* dx_bf16,
+                          float* dgamma, float* dbeta, int M, int d, void* stream);
+/* out[N](f32) (+)= column sums of a[M,N](bf16): bias gradients of nn.Linear                                  */
+int b200vit_colsum_bf16(const void* a, float* out, int M, int N, int accumulate, void* stream);
+int b200vit_colsum_f32(const float* a, float* out, int rows, int n, void* stream);
+int b200vit_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+
+/* ---- patch embedding (train_vit.py:34-45, blocks.py:235-237,257-267) ------------------------------------
+ * tokens[B, extra+P, d](f32): rows [0,extra) = extra_emb, rows [extra, ..) = conv(x) + bias + pos_emb.
+ * cols: caller-provided bf16 [B*P, C*p*p] im2col buffer (kept for the weight gradient).                     */
+int b200vit_patch_embed_fwd(const float* x, const void* w_bf16, const float* bias, const float* pos_emb,
+                            const float* extra_emb, float* tokens, void* cols, int B, int C, int H, int W, int p,
+                            int d, int extra, void* stream);
+/* dsum[T, d] = sum_b dtokens[b] ; dpe_bf16[B*P, d] = bf16(dtokens[:, extra:])                                */
+int b200vit_patch_embed_bwd_reduce(const float* dtokens, float* dsum, void* dpe_bf16, int B, int T, int extra,
+                                   int d, void* stream);
+int b200vit_im2col_bf16(const float* x, void* cols, int B, int C, int H, int W, int p, void* stream);
+int b200vit_col2im_f32(const void* dcols, float* dx, int B, int C, int H, int W, int p, void* stream);
+
+/* ---- VQ nearest-codebook lookup (train_titok.py:50-59 Quantizer; blocks.py:428-505 VectorQuantizer) -------
+ * x element (r, j) at x[(r / inner) * outer_stride + j * elem_stride + r % inner]  ([R,D]: 1,1,D ; bchw: hw,hw,chw)
+ * flags bit0: l2-normalise x and codes; bit1: gather normalised code rows (blocks.py) instead of raw rows.
+ * indices[R] int64 (bit-exact vs oracle/vq_oracle.c), quantized = xh + (c - xh) in x's layout,
+ * losses[3] = { mse, commitment_cost * mse, (1 + commitment_cost) * mse }.                                  */
+size_t b200vit_vq_workspace_size(long long R, int D, int K);
+int b200vit_vq_fwd(const float* x, const float* codebook, long long R, int D, int K, long long inner,
+                   long long elem_stride, long long outer_stride, int flags, float commitment_cost,
+                   long long* indices, float* quantized, float* losses, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* coef[2] (device): upstream scalars for d mean((c-xh)^2)/d xh and /d c ; dcodebook[K,D] is overwritten       */
+int b200vit_vq_bwd(const float* x, const float* codebook, const long long* indices, const float* grad_q,
+                   const float* coef, long long R, int D, int K, long long inner, long long elem_stride,
+                   long long outer_stride, int flags, float* dx, float* dcodebook, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

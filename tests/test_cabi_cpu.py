@@ -1,0 +1,37 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/b200vit.h declares; the binding table covers all of them; the product path refuses CPU tensors."""
+import ctypes
+
+import pytest
+import torch
+
+from b200vit import _cabi
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.load()
+    declared = _cabi.declared_symbols()
+    assert len(declared) >= 20
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"libb200vit.so does not export: {missing}"
+    assert lib.b200vit_version() == 100
+
+
+def test_binding_table_matches_header():
+    declared = set(_cabi.declared_symbols())
+    bound = set(_cabi._SIGNATURES) | {"b200vit_last_error"}
+    assert declared == bound, f"header-only: {declared - bound}; binding-only: {bound - declared}"
+
+
+def test_no_cpu_fallback():
+    from b200vit import ops
+    x = torch.zeros(8, 8, dtype=torch.bfloat16)
+    with pytest.raises(_cabi.B200VitError):
+        ops.gemm_bias(x, x, None)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a CPU-only box")
+def test_init_fails_loudly_without_gpu():
+    lib = _cabi.load()
+    assert lib.b200vit_init(ctypes.c_int(0)) != 0
+    assert len(lib.b200vit_last_error()) > 0

@@ -1,0 +1,249 @@
+"""Kernel-level parity on a real B200: every C-ABI op against the oracle (numpy / C) on the same seeded inputs.
+
+Tolerances (stated per test): bf16 outputs are compared with the oracle evaluated on the SAME bf16-rounded
+inputs, so the remaining error is fp32-accumulation order + one bf16 output rounding (rel 2^-8 = 3.9e-3);
+fp32 outputs to ~1e-5 relative; VQ indices and quantised values bit-exact."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+from oracle import vq_oracle as VQ
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from b200vit import ops as _ops
+    return _ops
+
+
+def bf16_round(a):
+    return torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+
+
+def to_dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def assert_close_bf16(got, ref, what, rel=1e-2):
+    got = got.float().cpu().numpy()
+    scale = np.abs(ref).max() + 1e-12
+    err = np.abs(got - ref).max() / scale
+    assert np.isfinite(got).all(), what
+    assert err < rel, f"{what}: max err / max|ref| = {err:.3e} (tol {rel})"
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (384, 768, 768), (1000, 2304, 768), (788, 192, 192),
+                                   (130, 128, 48), (2080, 576, 192), (77, 512, 2048)])
+def test_gemm_forward_family(ops, M, N, K):
+    rng = np.random.default_rng(M + N + K)
+    x = bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    w = bf16_round(rng.standard_normal((N, K)).astype(np.float32) * 0.05)
+    b = rng.standard_normal(N).astype(np.float32)
+    res = rng.standard_normal((M, N)).astype(np.float32)
+    ref = O.linear_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64))
+    xd, wd, bd = to_dev(x, torch.bfloat16), to_dev(w, torch.bfloat16), to_dev(b)
+    assert_close_bf16(ops.gemm_bias(xd, wd, bd), ref, "gemm_bias")
+    g, u = ops.gemm_bias_gelu(xd, wd, bd)
+    assert_close_bf16(u, ref, "gemm_bias_gelu.u")
+    assert_close_bf16(g, O.gelu_fwd(bf16_round(ref.astype(np.float32)).astype(np.float64)), "gemm_bias_gelu.g")
+    out = ops.gemm_bias_residual(xd, wd, bd, to_dev(res))
+    assert_close_bf16(out, ref + res, "gemm_bias_residual (fp32)", rel=2e-5)
+    out = ops.gemm_bias_f32(xd, wd, None)
+    assert_close_bf16(out, ref - b, "gemm_bias_f32", rel=2e-5)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 256), (256, 768, 768), (1000, 2304, 768), (788, 3072, 768), (520, 576, 192)])
+def test_gemm_dgrad_and_wgrad(ops, M, N, K):
+    rng = np.random.default_rng(M * 3 + N + K)
+    dy = bf16_round(rng.standard_normal((M, N)).astype(np.float32) * 0.1)
+    x = bf16_round(rng.standard_normal((M, K)).astype(np.float32) * 0.1)
+    w = bf16_round(rng.standard_normal((N, K)).astype(np.float32) * 0.05)
+    u = bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    dx_ref, dw_ref, _ = O.linear_bwd(dy.astype(np.float64), x.astype(np.float64), w.astype(np.float64))
+    dyd, xd, wd = to_dev(dy, torch.bfloat16), to_dev(x, torch.bfloat16), to_dev(w, torch.bfloat16)
+    assert_close_bf16(ops.gemm_dgrad(dyd, wd), dx_ref, "gemm_dgrad")
+    assert_close_bf16(ops.gemm_dgrad_dgelu(dyd, wd, to_dev(u, torch.bfloat16)), O.gelu_bwd(dx_ref, u.astype(np.float64)), "gemm_dgrad_dgelu")
+    dw = ops.gemm_wgrad(dyd, xd)
+    assert_close_bf16(dw, dw_ref, "gemm_wgrad (fp32, split-K atomics)", rel=2e-5)
+    dw2 = ops.gemm_wgrad(dyd, xd, out=dw.clone(), accumulate=True)
+    assert_close_bf16(dw2, 2 * dw_ref, "gemm_wgrad accumulate", rel=2e-5)
+    db = ops.colsum_bf16(dyd)
+    assert_close_bf16(db, dy.astype(np.float64).sum(0), "colsum_bf16", rel=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("M,d,affine", [(65 * 4, 192, False), (197 * 3, 768, False), (100, 1024, True), (289 * 2, 512, True), (7, 64, False)])
+def test_layernorm_fwd_bwd(ops, M, d, affine):
+    rng = np.random.default_rng(M + d)
+    x = rng.standard_normal((M, d)).astype(np.float32) * 2 + 0.5
+    add = bf16_round(rng.standard_normal((M, d)).astype(np.float32))
+    gamma = (1 + 0.1 * rng.standard_normal(d)).astype(np.float32) if affine else None
+    beta = (0.1 * rng.standard_normal(d)).astype(np.float32) if affine else None
+    dy = bf16_round(rng.standard_normal((M, d)).astype(np.float32))
+    dres = rng.standard_normal((M, d)).astype(np.float32)
+    x1 = x + add
+    y_ref, cache = O.layer_norm_fwd(x1.astype(np.float64), None if gamma is None else gamma.astype(np.float64),
+                                    None if beta is None else beta.astype(np.float64))
+    dx_ref, dg_ref, db_ref = O.layer_norm_bwd(dy.astype(np.float64), cache)
+    gd = None if gamma is None else to_dev(gamma)
+    bd = None if beta is None else to_dev(beta)
+    y, y32, mean, rstd, x_out = ops.layernorm_fwd(to_dev(x), add=to_dev(add, torch.bfloat16), gamma=gd, beta=bd,
+                                                  want_x_out=True, out_f32=True)
+    assert_close_bf16(x_out, x1, "x + add", rel=1e-6)
+    assert_close_bf16(y32, y_ref, "LN fwd fp32", rel=1e-5)
+    assert_close_bf16(y, y_ref, "LN fwd bf16", rel=5e-3)
+    assert_close_bf16(mean, x1.astype(np.float64).mean(-1), "mean", rel=1e-5)
+    dx, dxb, dg, db = ops.layernorm_bwd(to_dev(dy, torch.bfloat16), x_out, mean, rstd, gamma=gd, dres=to_dev(dres),
+                                        want_bf16=True, affine_grads=affine)
+    assert_close_bf16(dx, dx_ref + dres, "LN bwd dx", rel=2e-5)
+    assert_close_bf16(dxb, dx_ref + dres, "LN bwd dx bf16", rel=5e-3)
+    if affine:
+        assert_close_bf16(dg, dg_ref, "dgamma", rel=1e-4)
+        assert_close_bf16(db, db_ref, "dbeta", rel=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attn_case(ops, B, N, H, causal, seed):
+    rng = np.random.default_rng(seed)
+    d = H * 64
+    qkv = bf16_round(rng.standard_normal((B, N, 3, H, 64)).astype(np.float32))
+    do = bf16_round(rng.standard_normal((B, N, H, 64)).astype(np.float32))
+    q, k, v = (np.transpose(qkv[:, :, i], (0, 2, 1, 3)).astype(np.float64) for i in range(3))
+    o_ref, cache = O.sdpa_fwd(q, k, v, causal)
+    o, lse = ops.flash_attn_fwd(to_dev(qkv, torch.bfloat16), B, N, H, causal)
+    o_ref_bnd = np.transpose(o_ref, (0, 2, 1, 3)).reshape(B, N, d)
+    assert_close_bf16(o, o_ref_bnd, f"attention fwd B={B} N={N} H={H} causal={causal}", rel=1.5e-2)
+    s = (q @ np.swapaxes(k, -1, -2)) / 8.0
+    if causal:
+        s = np.where(np.triu(np.ones((N, N), dtype=bool), 1), -np.inf, s)
+    mx = s.max(-1, keepdims=True)
+    lse_ref = (mx + np.log(np.exp(s - mx).sum(-1, keepdims=True)))[..., 0]
+    assert_close_bf16(lse, lse_ref, "lse", rel=1e-4)
+    # backward: feed the kernel its own (bf16) o, as training does
+    dq_ref, dk_ref, dv_ref = O.sdpa_bwd(np.transpose(do, (0, 2, 1, 3)).astype(np.float64), cache)
+    dqkv_ref = np.stack([np.transpose(t, (0, 2, 1, 3)) for t in (dq_ref, dk_ref, dv_ref)], axis=2).reshape(B, N, 3 * d)
+    dqkv = ops.flash_attn_bwd(to_dev(qkv, torch.bfloat16), o, to_dev(do.reshape(B, N, d), torch.bfloat16), lse, B, N, H, causal)
+    got = dqkv.float().cpu().numpy()
+    for i, nm in enumerate(("dq", "dk", "dv")):
+        ref = dqkv_ref[:, :, i * d:(i + 1) * d]
+        err = np.abs(got[:, :, i * d:(i + 1) * d] - ref).max() / (np.abs(ref).max() + 1e-12)
+        assert err < 2e-2, f"attention bwd {nm} B={B} N={N} H={H} causal={causal}: {err:.3e}"
+
+
+@pytest.mark.parametrize("B,N,H,causal", [(2, 16, 1, False), (2, 65, 3, False), (1, 128, 2, False), (3, 197, 2, False),
+                                          (2, 257, 1, False), (2, 288, 2, False), (1, 320, 1, False),
+                                          (2, 16, 1, True), (1, 200, 2, True), (1, 1024, 1, True)])
+def test_flash_attention(ops, B, N, H, causal):
+    _attn_case(ops, B, N, H, causal, seed=N + H)
+
+
+# ------------------------------------------------------------------------------------------------ patch embed
+@pytest.mark.parametrize("B,C,H,p,d,extra", [(4, 3, 32, 4, 192, 1), (2, 3, 224, 16, 768, 1), (2, 3, 64, 8, 128, 0),
+                                             (3, 64, 8, 1, 64, 5)])
+def test_patch_embed(ops, B, C, H, p, d, extra):
+    rng = np.random.default_rng(B + C + H + p)
+    W = H if p > 1 else 1
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    P = (H // p) * (W // p)
+    conv_w = bf16_round(rng.standard_normal((d, C, p, p)).astype(np.float32) * 0.05)
+    conv_b = rng.standard_normal(d).astype(np.float32)
+    pos = rng.standard_normal((P, d)).astype(np.float32)
+    ext = rng.standard_normal((extra, d)).astype(np.float32)
+    ref, _ = O.patch_embed_fwd(bf16_round(x).astype(np.float64), conv_w.astype(np.float64), conv_b.astype(np.float64),
+                               pos.astype(np.float64), ext.astype(np.float64))
+    tokens, cols = ops.patch_embed_fwd(to_dev(x), to_dev(conv_w, torch.bfloat16), to_dev(conv_b), to_dev(pos),
+                                       to_dev(ext) if extra else None, p)
+    assert_close_bf16(tokens, ref, "patch embed tokens", rel=2e-5)
+    np.testing.assert_array_equal(cols.float().cpu().numpy().reshape(B, P, -1), O.im2col(bf16_round(x), p))
+    # backward helpers
+    dtok = rng.standard_normal((B, P + extra, d)).astype(np.float32)
+    dsum, dpe = ops.patch_embed_bwd_reduce(to_dev(dtok), extra)
+    assert_close_bf16(dsum, dtok.astype(np.float64).sum(0), "sum_b dtokens", rel=1e-5)
+    np.testing.assert_array_equal(dpe.float().cpu().numpy(), bf16_round(dtok[:, extra:].reshape(B * P, d)))
+    dx = ops.col2im(cols, B, C, H, W, p)
+    np.testing.assert_array_equal(dx.cpu().numpy(), bf16_round(x))
+
+
+# ------------------------------------------------------------------------------------------------ VQ
+def _vq_check(ops, x, cb, l2, gather_norm, channels_first, cc=0.25):
+    q_ref, idx_ref, mse_ref, dist_ref = VQ.vq_fwd(x, cb, l2=l2, gather_normalized=gather_norm,
+                                                  channels_first=channels_first, want_dist=True)
+    q, idx, losses = ops.vq_fwd(to_dev(x), to_dev(cb), l2=l2, gather_normalized=gather_norm,
+                                channels_first=channels_first, commitment_cost=cc)
+    idx = idx.cpu().numpy().reshape(idx_ref.shape)
+    assert np.array_equal(idx, idx_ref), f"VQ indices differ at {(idx != idx_ref).sum()} of {idx.size} rows"
+    assert np.array_equal(q.cpu().numpy(), q_ref), "quantised values must be bit-exact vs the C oracle"
+    ls = losses.cpu().numpy()
+    np.testing.assert_allclose(ls[0], mse_ref, rtol=1e-5)
+    np.testing.assert_allclose(ls[1], cc * mse_ref, rtol=1e-5)
+    np.testing.assert_allclose(ls[2], (1 + cc) * mse_ref, rtol=1e-5)
+    return idx
+
+
+def test_vq_golden_fixtures(ops, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "quantizer.npz"))
+    for tag in ("default", "trained", "small"):
+        idx = _vq_check(ops, g[f"{tag}_x"], g[f"{tag}_codebook"], True, False, False)
+        assert np.array_equal(idx, g[f"{tag}_indices"]), "indices must equal the reference Quantizer's"
+    g = np.load(os.path.join(golden_dir, "vector_quantizer.npz"))
+    for tag, l2 in (("l2", True), ("plain", False)):
+        idx = _vq_check(ops, g[f"{tag}_z"], g[f"{tag}_embedding"], l2, l2, True)
+        assert np.array_equal(idx, g[f"{tag}_indices"]), "indices must equal the reference VectorQuantizer's"
+
+
+@pytest.mark.parametrize("R,D,K", [(8192, 12, 4096), (16 * 16 * 64, 12, 1024), (1, 12, 4096), (33, 12, 7), (100, 4, 64),
+                                   (257, 8, 513), (64, 16, 2048), (50, 32, 300), (40, 64, 128), (31, 6, 1), (77, 20, 99)])
+def test_vq_shapes_bitexact(ops, R, D, K):
+    rng = np.random.default_rng(R + D + K)
+    x = rng.standard_normal((R, D)).astype(np.float32)
+    cb = rng.standard_normal((K, D)).astype(np.float32)
+    _vq_check(ops, x, cb, True, False, False)
+    _vq_check(ops, x, cb, False, False, False)
+    _vq_check(ops, x, cb, True, True, False)
+
+
+def test_vq_edge_cases(ops):
+    rng = np.random.default_rng(5)
+    # exact ties (duplicated codes): the lowest index must win, like torch.argmin
+    cb = rng.standard_normal((256, 12)).astype(np.float32)
+    cb[200] = cb[3]; cb[100] = cb[3]; cb[255] = cb[0]
+    x = rng.standard_normal((500, 12)).astype(np.float32)
+    x[:10] = cb[3] * 2.0
+    x[10:20] = cb[0] * 0.5
+    idx = _vq_check(ops, x, cb, True, False, False)
+    assert (idx[:10] == 3).all() and (idx[10:20] == 0).all()
+    # all-zero rows and a zero code hit the F.normalize eps clamp
+    x[20:25] = 0.0
+    cb[7] = 0.0
+    _vq_check(ops, x, cb, True, False, False)
+    # default-initialised (tiny uniform) codebook as in train_titok.py:49
+    cb = rng.uniform(-1 / 4096, 1 / 4096, size=(4096, 12)).astype(np.float32)
+    _vq_check(ops, x, cb, True, False, False)
+    # channels-first [b, c, h, w] layout of blocks.VectorQuantizer
+    z = rng.standard_normal((8, 12, 1, 32)).astype(np.float32)
+    _vq_check(ops, z, rng.standard_normal((4096, 12)).astype(np.float32), True, True, True)
+
+
+@pytest.mark.parametrize("l2,gn,cf", [(True, False, False), (True, True, True), (False, False, True)])
+def test_vq_backward(ops, l2, gn, cf):
+    rng = np.random.default_rng(17)
+    x = rng.standard_normal((16, 12, 1, 32) if cf else (16, 32, 12)).astype(np.float32)
+    cb = rng.standard_normal((512, 12)).astype(np.float32)
+    g = rng.standard_normal(x.shape).astype(np.float32)
+    _, idx_ref, _ = VQ.vq_fwd(x, cb, l2=l2, gather_normalized=gn, channels_first=cf)
+    dx_ref, dC_ref = VQ.vq_bwd(x, cb, idx_ref, g, 0.25 * 1.5, 1.5, l2=l2, gather_normalized=gn, channels_first=cf)
+    coef = torch.tensor([0.25 * 1.5, 1.5], device=DEV)
+    dx, dC = ops.vq_bwd(to_dev(x), to_dev(cb), to_dev(idx_ref.reshape(-1)), to_dev(g), coef, l2=l2,
+                        gather_normalized=gn, channels_first=cf)
+    np.testing.assert_allclose(dx.cpu().numpy(), dx_ref, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(dC.cpu().numpy(), dC_ref, rtol=1e-4, atol=1e-7)

@@ -1,0 +1,185 @@
+"""Pins the numpy oracle (oracle/vit_oracle.py) against fixtures produced by the reference modules
+themselves (tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import vit_oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _close(a, b, rtol=2e-4, atol=2e-5):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def _layer_params(g, prefix, i):
+    k = f"{prefix}layers.{i}."
+    return {
+        "qkv_w": g[k + "multi_attn.qkv.weight"], "qkv_b": g[k + "multi_attn.qkv.bias"],
+        "fc1_w": g[k + "mlp.0.weight"], "fc1_b": g[k + "mlp.0.bias"],
+        "fc2_w": g[k + "mlp.2.weight"], "fc2_b": g[k + "mlp.2.bias"],
+    }
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_transformer_fwd_bwd(golden_dir, tag):
+    g = _load(golden_dir, "transformer.npz")
+    L, h, d, N, B, causal = (int(v) for v in g[f"{tag}_cfg"])
+    layers = [_layer_params(g, f"{tag}_w_", i) for i in range(L)]
+    y, caches = O.transformer_fwd(g[f"{tag}_x"], layers, h, bool(causal))
+    _close(y, g[f"{tag}_y"])
+    dx, grads = O.transformer_bwd(g[f"{tag}_dy"], caches)
+    _close(dx, g[f"{tag}_dx"])
+    names = {"qkv_w": "multi_attn.qkv.weight", "qkv_b": "multi_attn.qkv.bias", "fc1_w": "mlp.0.weight",
+             "fc1_b": "mlp.0.bias", "fc2_w": "mlp.2.weight", "fc2_b": "mlp.2.bias"}
+    for i in range(L):
+        for k, ref in names.items():
+            _close(grads[i][k], g[f"{tag}_g_layers.{i}.{ref}"], rtol=5e-4, atol=5e-5)
+
+
+def _vit_params(g, prefix, n_layers):
+    return {
+        "conv_w": g[prefix + "vit.patch_proj.weight"], "conv_b": g[prefix + "vit.patch_proj.bias"],
+        "pos_emb": g[prefix + "vit.pos_emb.weight"], "extra_emb": g[prefix + "vit.extra_emb.weight"],
+        "layers": [_layer_params(g, prefix + "vit.transformer.", i) for i in range(n_layers)],
+        "head_w": g[prefix + "head.weight"], "head_b": g[prefix + "head.bias"],
+    }
+
+
+def test_vit_classifier_step_xs(golden_dir):
+    g = _load(golden_dir, "vit.npz")
+    P = _vit_params(g, "xs_w_", 2)
+    tokens, _ = O.vit_fwd(g["xs_x"], P, n_heads=1)
+    _close(tokens, g["xs_tokens"])
+    loss, logits, grads = O.vit_classifier_loss_and_grads(g["xs_x"], g["xs_labels"], P, n_heads=1)
+    _close(logits, g["xs_logits"])
+    _close(loss, g["xs_loss"])
+    _close(grads["conv_w"], g["xs_g_vit.patch_proj.weight"], rtol=1e-3, atol=1e-5)
+    _close(grads["conv_b"], g["xs_g_vit.patch_proj.bias"], rtol=1e-3, atol=1e-5)
+    _close(grads["pos_emb"], g["xs_g_vit.pos_emb.weight"], rtol=1e-3, atol=1e-5)
+    _close(grads["extra_emb"], g["xs_g_vit.extra_emb.weight"], rtol=1e-3, atol=1e-5)
+    _close(grads["head_w"], g["xs_g_head.weight"], rtol=1e-3, atol=1e-5)
+    _close(grads["layers"][0]["qkv_w"], g["xs_g_vit.transformer.layers.0.multi_attn.qkv.weight"], rtol=1e-3, atol=1e-5)
+    _close(grads["layers"][1]["fc2_w"], g["xs_g_vit.transformer.layers.1.mlp.2.weight"], rtol=1e-3, atol=1e-5)
+
+
+def det_weights_np(shapes, seed, scale):
+    """Same recipe as tests/golden/make_golden.py:det_weights (numpy Generator in state_dict order)."""
+    rng = np.random.default_rng(seed)
+    return {k: rng.standard_normal(s).astype(np.float32) * scale for k, s in shapes}
+
+
+def vit_ti_shapes(n_classes=10, d=192, L=12, C=3, p=4, P=64, extra=1):
+    shapes = [("vit.patch_proj.weight", (d, C, p, p)), ("vit.patch_proj.bias", (d,)),
+              ("vit.pos_emb.weight", (P, d)), ("vit.extra_emb.weight", (extra, d))]
+    for i in range(L):
+        k = f"vit.transformer.layers.{i}."
+        shapes += [(k + "multi_attn.qkv.weight", (3 * d, d)), (k + "multi_attn.qkv.bias", (3 * d,)),
+                   (k + "mlp.0.weight", (4 * d, d)), (k + "mlp.0.bias", (4 * d,)),
+                   (k + "mlp.2.weight", (d, 4 * d)), (k + "mlp.2.bias", (d,))]
+    shapes += [("head.weight", (n_classes, d)), ("head.bias", (n_classes,))]
+    return shapes
+
+
+def test_vit_tiny_baseline_config1(golden_dir):
+    """BASELINE.json configs[0]: ViT-Ti (192/12/3), patch 4, 32x32, batch 32, fwd + CE + bwd on CPU."""
+    g = _load(golden_dir, "vit.npz")
+    w = det_weights_np(vit_ti_shapes(), seed=1, scale=0.03)
+    P = _vit_params({("ti_w_" + k): v for k, v in w.items()}, "ti_w_", 12)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((32, 3, 32, 32)).astype(np.float32)
+    labels = rng.integers(0, 10, size=(32,))
+    loss, logits, grads = O.vit_classifier_loss_and_grads(x, labels, P, n_heads=3)
+    _close(logits, g["ti_logits"], rtol=1e-3, atol=1e-4)
+    _close(loss, g["ti_loss"], rtol=1e-4)
+    flat = {"vit.patch_proj.weight": grads["conv_w"], "vit.patch_proj.bias": grads["conv_b"],
+            "vit.pos_emb.weight": grads["pos_emb"], "vit.extra_emb.weight": grads["extra_emb"],
+            "head.weight": grads["head_w"], "head.bias": grads["head_b"]}
+    m = {"qkv_w": "multi_attn.qkv.weight", "qkv_b": "multi_attn.qkv.bias", "fc1_w": "mlp.0.weight",
+         "fc1_b": "mlp.0.bias", "fc2_w": "mlp.2.weight", "fc2_b": "mlp.2.bias"}
+    for i in range(12):
+        for k, ref in m.items():
+            flat[f"vit.transformer.layers.{i}.{ref}"] = grads["layers"][i][k]
+    for name, norm, sample in zip(g["ti_grad_names"], g["ti_grad_norms"], g["ti_grad_samples"]):
+        got = flat[str(name)]
+        np.testing.assert_allclose(np.linalg.norm(got.astype(np.float64)), norm, rtol=2e-3)
+        np.testing.assert_allclose(got.reshape(-1)[:8], sample, rtol=5e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["default", "trained", "small"])
+def test_quantizer(golden_dir, tag):
+    g = _load(golden_dir, "quantizer.npz")
+    q, idx, loss, cache = O.quantizer_fwd(g[f"{tag}_x"], g[f"{tag}_codebook"])
+    assert np.array_equal(idx, g[f"{tag}_indices"]), "VQ indices must be bit-exact"
+    _close(q, g[f"{tag}_quantized"], rtol=0, atol=3e-7)
+    _close(loss, g[f"{tag}_loss"], rtol=1e-5, atol=0)
+    dx, dC = O.quantizer_bwd(g[f"{tag}_dq"], float(g[f"{tag}_dloss"]), cache)
+    _close(dx, g[f"{tag}_dx"], rtol=1e-4, atol=1e-6)
+    _close(dC, g[f"{tag}_dC"], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag,l2", [("l2", True), ("plain", False)])
+def test_vector_quantizer(golden_dir, tag, l2):
+    g = _load(golden_dir, "vector_quantizer.npz")
+    zq, loss, closs, cbloss, idx, cache = O.vector_quantizer_fwd(g[f"{tag}_z"], g[f"{tag}_embedding"], 0.25, l2)
+    assert np.array_equal(idx, g[f"{tag}_indices"]), "VQ indices must be bit-exact"
+    _close(zq, g[f"{tag}_zq"], rtol=0, atol=5e-7)
+    _close(loss, g[f"{tag}_loss"], rtol=1e-5)
+    _close(closs, g[f"{tag}_commitment_loss"], rtol=1e-5)
+    _close(cbloss, g[f"{tag}_codebook_loss"], rtol=1e-5)
+    dz, dE = O.vector_quantizer_bwd(g[f"{tag}_dz"], 2.0, cache)
+    _close(dz, g[f"{tag}_dzin"], rtol=1e-4, atol=1e-6)
+    _close(dE, g[f"{tag}_dE"], rtol=1e-4, atol=1e-7)
+
+
+def test_residual_attention_block(golden_dir):
+    g = _load(golden_dir, "resblock.npz")
+    d, h, L, B = (int(v) for v in g["cfg"])
+    p = {"ln1_w": g["w_ln_1.weight"], "ln1_b": g["w_ln_1.bias"], "in_w": g["w_attn.in_proj_weight"],
+         "in_b": g["w_attn.in_proj_bias"], "out_w": g["w_attn.out_proj.weight"], "out_b": g["w_attn.out_proj.bias"],
+         "ln2_w": g["w_ln_2.weight"], "ln2_b": g["w_ln_2.bias"], "fc_w": g["w_mlp.c_fc.weight"],
+         "fc_b": g["w_mlp.c_fc.bias"], "proj_w": g["w_mlp.c_proj.weight"], "proj_b": g["w_mlp.c_proj.bias"]}
+    y, cache = O.residual_attention_block_fwd(g["x"], p, h)
+    _close(y, g["y"])
+    dx, gr = O.residual_attention_block_bwd(g["dy"], cache)
+    _close(dx, g["dx"], rtol=5e-4, atol=5e-5)
+    ref = {"ln1_w": "ln_1.weight", "ln1_b": "ln_1.bias", "in_w": "attn.in_proj_weight", "in_b": "attn.in_proj_bias",
+           "out_w": "attn.out_proj.weight", "out_b": "attn.out_proj.bias", "ln2_w": "ln_2.weight",
+           "ln2_b": "ln_2.bias", "fc_w": "mlp.c_fc.weight", "fc_b": "mlp.c_fc.bias",
+           "proj_w": "mlp.c_proj.weight", "proj_b": "mlp.c_proj.bias"}
+    for k, r in ref.items():
+        _close(gr[k], g[f"g_{r}"], rtol=1e-3, atol=5e-5)
+
+
+# ---- the C oracle (bit-exact fp32 spec of the VQ lookup) against the same reference fixtures ----
+from oracle import vq_oracle as VQ  # noqa: E402
+
+
+@pytest.mark.parametrize("tag", ["default", "trained", "small"])
+def test_c_oracle_quantizer(golden_dir, tag):
+    g = _load(golden_dir, "quantizer.npz")
+    q, idx, mse = VQ.vq_fwd(g[f"{tag}_x"], g[f"{tag}_codebook"], l2=True, gather_normalized=False)
+    assert np.array_equal(idx, g[f"{tag}_indices"]), "C oracle indices must equal the reference's argmin"
+    _close(q, g[f"{tag}_quantized"], rtol=0, atol=3e-7)
+    _close(np.float32(1.25 * mse), g[f"{tag}_loss"], rtol=1e-5, atol=0)
+    dL = float(g[f"{tag}_dloss"])
+    dx, dC = VQ.vq_bwd(g[f"{tag}_x"], g[f"{tag}_codebook"], idx, g[f"{tag}_dq"], 0.25 * dL, dL)
+    _close(dx, g[f"{tag}_dx"], rtol=1e-4, atol=1e-6)
+    _close(dC, g[f"{tag}_dC"], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag,l2", [("l2", True), ("plain", False)])
+def test_c_oracle_vector_quantizer(golden_dir, tag, l2):
+    g = _load(golden_dir, "vector_quantizer.npz")
+    q, idx, mse = VQ.vq_fwd(g[f"{tag}_z"], g[f"{tag}_embedding"], l2=l2, gather_normalized=l2, channels_first=True)
+    assert np.array_equal(idx, g[f"{tag}_indices"])
+    _close(q, g[f"{tag}_zq"], rtol=0, atol=5e-7)
+    _close(np.float32(1.25 * mse), g[f"{tag}_loss"], rtol=1e-5)
+    dz, dE = VQ.vq_bwd(g[f"{tag}_z"], g[f"{tag}_embedding"], idx, g[f"{tag}_dz"], 0.25 * 2.0, 2.0, l2=l2,
+                       gather_normalized=l2, channels_first=True)
+    _close(dz, g[f"{tag}_dzin"], rtol=1e-4, atol=1e-6)
+    _close(dE, g[f"{tag}_dE"], rtol=1e-4, atol=1e-7)

@@ -33,6 +33,45 @@ def declared_symbols(header_path: str = HEADER_PATH):
     return sorted(set(re.findall(r"\b(b200vit_[a-z0-9_]+)\s*\(", text)))
 
 
+_P, _I, _L, _F, _Z = c_void_p, c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
+
+# argument types of every entry point in include/b200vit.h (ctypes would otherwise guess c_int for ints)
+_SIGNATURES = {
+    "b200vit_init": (_I, [_I]),
+    "b200vit_version": (_I, []),
+    "b200vit_debug_set": (_I, [_I, _I]),
+    "b200vit_gemm_bias": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200vit_gemm_bias_gelu": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200vit_gemm_bias_residual": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200vit_gemm_bias_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200vit_gemm_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "b200vit_gemm_dgrad_dgelu": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200vit_gemm_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200vit_flash_attn_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200vit_flash_attn_bwd_workspace_size": (_Z, [_I, _I, _I]),
+    "b200vit_flash_attn_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
+    "b200vit_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
+    "b200vit_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "b200vit_colsum_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
+    "b200vit_colsum_f32": (_I, [_P, _P, _I, _I, _P]),
+    "b200vit_cast_f32_bf16": (_I, [_P, _P, _L, _P]),
+    "b200vit_patch_embed_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b200vit_patch_embed_bwd_reduce": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200vit_im2col_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200vit_col2im_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200vit_vq_workspace_size": (_Z, [_L, _I, _I]),
+    "b200vit_vq_fwd": (_I, [_P, _P, _L, _I, _I, _L, _L, _L, _I, _F, _P, _P, _P, _P, _Z, _P]),
+    "b200vit_vq_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _L, _L, _L, _I, _P, _P, _P]),
+}
+
+
+def _declare(lib):
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+
+
 def load():
     """Loads the library once; raises loudly when it has not been built."""
     global _lib
@@ -47,6 +86,7 @@ def load():
                 " There is no CPU / PyTorch fallback for the b200vit hot path.")
         lib = ctypes.CDLL(LIB_PATH)
         lib.b200vit_last_error.restype = ctypes.c_char_p
+        _declare(lib)
         _lib = lib
     return _lib
 

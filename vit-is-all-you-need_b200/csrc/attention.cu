@@ -1,0 +1,565 @@
+// Fused flash-style multi-head self-attention for head_dim = 64 (every config of the reference:
+// transformer.py:56-58, blocks.py:219-233), forward and backward, on tcgen05 tensor cores.
+//
+// Replaces F.scaled_dot_product_attention(q, k, v, attn_mask=None | -inf upper triangle) at
+// transformer.py:28 (and the SDPA inside nn.MultiheadAttention, blocks.py:60) together with the
+// "b n (qkv h d) -> qkv b h n d" / "b h n d -> b n (h d)" rearranges (transformer.py:27,29): Q, K, V are
+// read straight out of the packed QKV GEMM output [B, N, 3, H, 64] by strided TMA boxes and O is written as
+// [B, N, H*64]; the [N, N] score matrix never touches HBM (the reference materialises an additive mask
+// buffer [block, block], transformer.py:22-25).
+//
+// Forward, per CTA = (batch, head, 128-query tile), looping over 128-key blocks with online softmax:
+//   S = Q K^T   tcgen05.mma, both operands K-major from TMA tiles, fp32 S in TMEM
+//   softmax     4 warps, one query row per thread (TMEM lane == row), exp2 with fp32 running max / sum
+//   O_j = P V   P written as bf16 to a 128B-swizzled smem tile (K-major A), V used as an MN-major B
+// Backward, per CTA = (batch, head, 128-key block), looping over 128-query tiles:
+//   S = Q K^T, dP = dO V^T, P = exp2(S - lse), dS = P (dP - D) scale,
+//   dV += P^T dO, dK += dS^T Q (accumulated in TMEM), dQ = dS K (fp32 atomics, converted afterwards).
+#include "../../include/b200vit.h"
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int AT_HD = 64;
+constexpr int AT_BQ = 128;
+constexpr int AT_BK = 128;
+constexpr int AT_THREADS = 192;        // warps 0-3: softmax/compute, warp 4: TMA, warp 5: MMA + TMEM alloc
+constexpr int AT_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16 = 16 KB
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct AttnParams {
+  int B, N, H, d;
+  int causal;
+  float scale;          // 1/sqrt(64)
+  float scale_log2e;    // scale * log2(e)
+  __nv_bfloat16* o;     // [B, N, d]
+  float* lse;           // [B, H, N]  natural-log LSE of the scaled scores
+  // backward only
+  const __nv_bfloat16* o_in;   // [B, N, d]
+  const __nv_bfloat16* do_in;  // [B, N, d]
+  float* dq_acc;               // [B, N, d] fp32, zeroed
+  __nv_bfloat16* dqkv;         // [B, N, 3d]
+};
+
+// K-major SWIZZLE_128B tile (rows of 128 bytes): descriptor for the 16-element K slice `k16` (0..3)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k16) {
+  return umma_smem_desc(tile_addr + k16 * 32, 16, 1024);
+}
+// MN-major view of the same bytes: K advances by 16 rows (2048 B); `lbo` = distance between 64-wide MN groups
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int k16, uint32_t lbo) {
+  return umma_smem_desc(tile_addr + k16 * 2048, lbo, 1024);
+}
+
+// Writes 32 bf16 (already packed as 16 x b32) of row `row` into a [128 x 128] bf16 operand tile laid out as two
+// 64-column slabs of 128 rows x 128 bytes with the TMA 128B swizzle; `c32` in [0,4) selects the 32-column chunk.
+__device__ __forceinline__ void store_operand_chunk(uint8_t* tile, int row, int c32, const uint32_t (&w)[16]) {
+  uint8_t* slab = tile + (c32 >> 1) * (128 * 128) + row * 128;
+  const int chunk0 = (c32 & 1) * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int chunk = (chunk0 + q) ^ (row & 7);
+    *reinterpret_cast<uint4*>(slab + chunk * 16) = make_uint4(w[q * 4 + 0], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Forward
+// --------------------------------------------------------------------------------------------------
+struct FwdSmem {
+  static constexpr int Q = 0;
+  static constexpr int KV = AT_TILE_BYTES;                  // 2 stages x (K | V)
+  static constexpr int P = KV + 4 * AT_TILE_BYTES;          // 128 x 128 bf16 = 32 KB
+  static constexpr int BAR = P + 2 * AT_TILE_BYTES;
+  static constexpr int TOTAL = BAR + 128 + 1024;            // + alignment slack
+};
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
+  extern __shared__ uint8_t at_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * AT_BQ;
+  int nkv = (p.N + AT_BK - 1) / AT_BK;
+  if (CAUSAL) nkv = min(nkv, (q0 + AT_BQ + AT_BK - 1) / AT_BK);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // 128 columns
+  const uint32_t tmem_O = tmem_base + 128;  // 64 columns
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, AT_TILE_BYTES);
+      tma_load_3d(smem + FwdSmem::Q, &tm_qkv, q_full, hh * AT_HD, q0, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1, 10);
+        uint8_t* kdst = smem + FwdSmem::KV + st * 2 * AT_TILE_BYTES;
+        mbar_expect_tx(&kv_full[st], 2 * AT_TILE_BYTES);
+        tma_load_3d(kdst, &tm_qkv, &kv_full[st], p.d + hh * AT_HD, j * AT_BK, b);
+        tma_load_3d(kdst + AT_TILE_BYTES, &tm_qkv, &kv_full[st], 2 * p.d + hh * AT_HD, j * AT_BK, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, AT_BK, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, AT_HD, false, true);
+      const uint32_t sQ = smem_u32(smem + FwdSmem::Q);
+      const uint32_t sP = smem_u32(smem + FwdSmem::P);
+      mbar_wait(q_full, 0, 20);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t sK = smem_u32(smem + FwdSmem::KV + st * 2 * AT_TILE_BYTES);
+        const uint32_t sV = sK + AT_TILE_BYTES;
+        mbar_wait(&kv_full[st], (j >> 1) & 1, 21);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0);
+        umma_commit(s_full);
+        mbar_wait(p_ready, j & 1, 22);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_O, desc_kmajor(sP + (k >> 2) * AT_TILE_BYTES, k & 3), desc_mnmajor(sV, k, 8192), idesc_o, k > 0);
+        umma_commit(o_full);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    // ---- softmax warps: thread <-> query row ----
+    const int r = threadIdx.x;  // 0..127 == TMEM lane
+    const int q = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    float oacc[AT_HD];
+#pragma unroll
+    for (int i = 0; i < AT_HD; ++i) oacc[i] = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1, 30);
+        tc_fence_after();
+        uint32_t v[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(tmem_O + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) oacc[c * 32 + i] += __uint_as_float(v[i]);
+        }
+      }
+      mbar_wait(s_full, j & 1, 31);
+      tc_fence_after();
+      const bool need_mask = ((j + 1) * AT_BK > p.N) || (CAUSAL && (j + 1) * AT_BK > q0 + 1);
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = j * AT_BK + c * 32 + i;
+            const bool ok = key < p.N && (!CAUSAL || key <= q);
+            mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      float m_new = fmaxf(m, mx * p.scale_log2e);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f(m - m_use);
+      l *= alpha;
+#pragma unroll
+      for (int i = 0; i < AT_HD; ++i) oacc[i] *= alpha;
+      // pass 2: probabilities -> bf16 operand tile
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2e, -m_use));
+          float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, -m_use));
+          if (need_mask) {
+            const int key = j * AT_BK + c * 32 + i;
+            if (!(key < p.N && (!CAUSAL || key <= q))) p0 = 0.f;
+            if (!(key + 1 < p.N && (!CAUSAL || key + 1 <= q))) p1 = 0.f;
+          }
+          rowsum += p0 + p1;
+          w[i >> 1] = pack_bf16(p0, p1);
+        }
+        store_operand_chunk(smem + FwdSmem::P, r, c, w);
+      }
+      l += rowsum;
+      m = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // last PV
+    mbar_wait(o_full, (nkv - 1) & 1, 32);
+    tc_fence_after();
+    {
+      uint32_t v[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tmem_ld32(tmem_O + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) oacc[c * 32 + i] += __uint_as_float(v[i]);
+      }
+    }
+    if (q < p.N) {
+      const float inv = 1.0f / l;
+      __nv_bfloat16* orow = p.o + ((long long)b * p.N + q) * p.d + hh * AT_HD;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 w;
+        w.x = pack_bf16(oacc[c * 8 + 0] * inv, oacc[c * 8 + 1] * inv);
+        w.y = pack_bf16(oacc[c * 8 + 2] * inv, oacc[c * 8 + 3] * inv);
+        w.z = pack_bf16(oacc[c * 8 + 4] * inv, oacc[c * 8 + 5] * inv);
+        w.w = pack_bf16(oacc[c * 8 + 6] * inv, oacc[c * 8 + 7] * inv);
+        reinterpret_cast<uint4*>(orow)[c] = w;
+      }
+      if (p.lse != nullptr) p.lse[((long long)b * p.H + hh) * p.N + q] = m * LN2 + logf(l);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// --------------------------------------------------------------------------------------------------
+// Backward
+// --------------------------------------------------------------------------------------------------
+struct BwdSmem {
+  static constexpr int K = 0;
+  static constexpr int V = AT_TILE_BYTES;
+  static constexpr int QDO = 2 * AT_TILE_BYTES;             // 2 stages x (Q | dO)
+  static constexpr int P = QDO + 4 * AT_TILE_BYTES;         // 32 KB
+  static constexpr int DS = P + 2 * AT_TILE_BYTES;          // 32 KB
+  static constexpr int BAR = DS + 2 * AT_TILE_BYTES;
+  static constexpr int TOTAL = BAR + 128 + 1024;
+};
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const AttnParams p) {
+  extern __shared__ uint8_t at_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BAR);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* q_full = bars + 1;    // [2]
+  uint64_t* q_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_ready = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint64_t* dq_free = bars + 8;
+  uint64_t* dkv_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jb = blockIdx.x, hh = blockIdx.y, b = blockIdx.z;
+  const int k0 = jb * AT_BK;
+  const int nq = (p.N + AT_BQ - 1) / AT_BQ;
+  const int i0 = CAUSAL ? jb : 0;  // first query tile that sees this key block
+  const int ntiles = nq - i0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(kv_full, 1);
+    mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
+    mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_ready, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 128);
+    mbar_init(dkv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256,
+                 tmem_dK = tmem_base + 320, tmem_dQ = tmem_base + 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * AT_TILE_BYTES);
+      tma_load_3d(smem + BwdSmem::K, &tm_qkv, kv_full, p.d + hh * AT_HD, k0, b);
+      tma_load_3d(smem + BwdSmem::V, &tm_qkv, kv_full, 2 * p.d + hh * AT_HD, k0, b);
+      for (int it = 0; it < ntiles; ++it) {
+        const int st = it & 1;
+        mbar_wait(&q_empty[st], ((it >> 1) & 1) ^ 1, 40);
+        uint8_t* dst = smem + BwdSmem::QDO + st * 2 * AT_TILE_BYTES;
+        mbar_expect_tx(&q_full[st], 2 * AT_TILE_BYTES);
+        tma_load_3d(dst, &tm_qkv, &q_full[st], hh * AT_HD, (i0 + it) * AT_BQ, b);
+        tma_load_3d(dst + AT_TILE_BYTES, &tm_do, &q_full[st], hh * AT_HD, (i0 + it) * AT_BQ, b);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, AT_BK, false, false);   // S, dP: K-major x K-major
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, AT_HD, true, true);     // dV, dK: MN-major x MN-major
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, AT_HD, false, true);    // dQ: K-major x MN-major
+      const uint32_t sK = smem_u32(smem + BwdSmem::K), sV = smem_u32(smem + BwdSmem::V);
+      const uint32_t sP = smem_u32(smem + BwdSmem::P), sDS = smem_u32(smem + BwdSmem::DS);
+      mbar_wait(kv_full, 0, 50);
+      for (int it = 0; it < ntiles; ++it) {
+        const int st = it & 1;
+        const uint32_t sQ = smem_u32(smem + BwdSmem::QDO + st * 2 * AT_TILE_BYTES);
+        const uint32_t sDO = sQ + AT_TILE_BYTES;
+        mbar_wait(&q_full[st], (it >> 1) & 1, 51);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_dP, desc_kmajor(sDO, k), desc_kmajor(sV, k), idesc_s, k > 0);
+        umma_commit(sdp_full);
+        mbar_wait(pds_ready, it & 1, 52);
+        tc_fence_after();
+        // dV[key, d] += P^T dO ; dK[key, d] += dS^T Q   (contraction over the 128 query rows)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_dV, desc_mnmajor(sP, k, 16384), desc_mnmajor(sDO, k, 8192), idesc_t, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_dK, desc_mnmajor(sDS, k, 16384), desc_mnmajor(sQ, k, 8192), idesc_t, (it > 0 || k > 0) ? 1u : 0u);
+        if (it > 0) { mbar_wait(dq_free, (it - 1) & 1, 53); tc_fence_after(); }
+        // dQ[q, d] = dS K   (contraction over the 128 keys)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_dQ, desc_kmajor(sDS + (k >> 2) * AT_TILE_BYTES, k & 3), desc_mnmajor(sK, k, 8192), idesc_q, k > 0);
+        umma_commit(dq_full);
+        umma_commit(&q_empty[st]);
+      }
+      umma_commit(dkv_full);
+    }
+  } else {
+    const int r = threadIdx.x;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    for (int it = 0; it < ntiles; ++it) {
+      const int q = (i0 + it) * AT_BQ + r;
+      const bool qv = q < p.N;
+      float lse2 = 0.f, Dq = 0.f;
+      if (qv) {
+        lse2 = p.lse[((long long)b * p.H + hh) * p.N + q] * LOG2E;
+        const uint4* orow = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.N + q) * p.d + hh * AT_HD);
+        const uint4* drow = reinterpret_cast<const uint4*>(p.do_in + ((long long)b * p.N + q) * p.d + hh * AT_HD);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = orow[c], g = drow[c];
+          const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+          const float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
+          Dq += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+        }
+      }
+      mbar_wait(sdp_full, it & 1, 60);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], dp[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, s);
+        tmem_ld32(tmem_dP + lane_off + c * 32, dp);
+        tmem_ld_wait();
+        uint32_t wp[16], wd[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int key = k0 + c * 32 + i + e;
+            const bool ok = qv && key < p.N && (!CAUSAL || key <= q);
+            const float pe = ok ? exp2f(fmaf(__uint_as_float(s[i + e]), p.scale_log2e, -lse2)) : 0.f;
+            pv[e] = pe;
+            dv[e] = pe * (__uint_as_float(dp[i + e]) - Dq) * p.scale;
+          }
+          wp[i >> 1] = pack_bf16(pv[0], pv[1]);
+          wd[i >> 1] = pack_bf16(dv[0], dv[1]);
+        }
+        store_operand_chunk(smem + BwdSmem::P, r, c, wp);
+        store_operand_chunk(smem + BwdSmem::DS, r, c, wd);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_ready);
+
+      mbar_wait(dq_full, it & 1, 61);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_dQ + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (qv) {
+          float* dst = p.dq_acc + ((long long)b * p.N + q) * p.d + hh * AT_HD + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            atomicAdd(reinterpret_cast<float4*>(dst + i),
+                      make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_free);
+    }
+    // dK / dV of this key block
+    mbar_wait(dkv_full, 0, 62);
+    tc_fence_after();
+    const int key = k0 + r;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {  // 0: dK, 1: dV
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (key < p.N) {
+          __nv_bfloat16* dst = p.dqkv + ((long long)b * p.N + key) * 3 * p.d + (which + 1) * p.d + hh * AT_HD + c * 32;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(v[i * 8 + 0]), __uint_as_float(v[i * 8 + 1]));
+            w.y = pack_bf16(__uint_as_float(v[i * 8 + 2]), __uint_as_float(v[i * 8 + 3]));
+            w.z = pack_bf16(__uint_as_float(v[i * 8 + 4]), __uint_as_float(v[i * 8 + 5]));
+            w.w = pack_bf16(__uint_as_float(v[i * 8 + 6]), __uint_as_float(v[i * 8 + 7]));
+            reinterpret_cast<uint4*>(dst)[i] = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// dq_acc fp32 [rows, d] -> bf16 into dqkv[:, 0:d] (row pitch 3d)
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
+                                       long long rows, int d) {
+  const long long nvec = rows * (d / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / (d / 4);
+    const int c = (int)(i - row * (d / 4)) * 4;
+    const float4 v = reinterpret_cast<const float4*>(acc)[i];
+    uint2 w;
+    w.x = pack_bf16(v.x, v.y); w.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(dqkv + row * 3 * d + c) = w;
+  }
+}
+
+static int make_tmap_bnd(CUtensorMap* tm, const void* base, int B, int N, int row_elems) {
+  const uint64_t dims[3] = {(uint64_t)row_elems, (uint64_t)N, (uint64_t)B};
+  const uint64_t strides[3] = {2, (uint64_t)row_elems * 2, (uint64_t)N * row_elems * 2};
+  const uint32_t box[3] = {64, 128, 1};
+  return make_tmap_nd_bf16(tm, base, 3, dims, strides, box, true);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int causal,
+                           void* stream) {
+  B200_REQUIRE(qkv && o, "flash_attn_fwd: null pointer");
+  B200_REQUIRE(B > 0 && N > 0 && H > 0, "flash_attn_fwd: bad sizes");
+  const int d = H * AT_HD;
+  CUtensorMap tm;
+  int rc = make_tmap_bnd(&tm, qkv, B, N, 3 * d);
+  if (rc != OK) return rc;
+  AttnParams p{};
+  p.B = B; p.N = N; p.H = H; p.d = d; p.causal = causal;
+  p.scale = 0.125f; p.scale_log2e = 0.125f * LOG2E;
+  p.o = (__nv_bfloat16*)o; p.lse = lse;
+  dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (causal) {
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+    attn_fwd_kernel<true><<<grid, AT_THREADS, FwdSmem::TOTAL, st>>>(tm, p);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
+    attn_fwd_kernel<false><<<grid, AT_THREADS, FwdSmem::TOTAL, st>>>(tm, p);
+  }
+  B200_CUDA(cudaGetLastError());
+  return OK;
+}
+
+size_t b200vit_flash_attn_bwd_workspace_size(int B, int N, int H) {
+  return (size_t)B * N * H * AT_HD * sizeof(float);
+}
+
+int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
+                           int B, int N, int H, int causal, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  B200_REQUIRE(qkv && o && d_o && lse && dqkv && workspace, "flash_attn_bwd: null pointer");
+  B200_REQUIRE(workspace_bytes >= b200vit_flash_attn_bwd_workspace_size(B, N, H), "flash_attn_bwd: workspace too small");
+  const int d = H * AT_HD;
+  CUtensorMap tm_qkv, tm_do;
+  int rc = make_tmap_bnd(&tm_qkv, qkv, B, N, 3 * d);
+  if (rc != OK) return rc;
+  rc = make_tmap_bnd(&tm_do, d_o, B, N, d);
+  if (rc != OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  AttnParams p{};
+  p.B = B; p.N = N; p.H = H; p.d = d; p.causal = causal;
+  p.scale = 0.125f; p.scale_log2e = 0.125f * LOG2E;
+  p.lse = const_cast<float*>(lse);
+  p.o_in = (const __nv_bfloat16*)o; p.do_in = (const __nv_bfloat16*)d_o;
+  p.dq_acc = (float*)workspace; p.dqkv = (__nv_bfloat16*)dqkv;
+  B200_CUDA(cudaMemsetAsync(workspace, 0, b200vit_flash_attn_bwd_workspace_size(B, N, H), st));
+  dim3 grid((N + AT_BK - 1) / AT_BK, H, B);
+  if (causal) {
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
+    attn_bwd_kernel<true><<<grid, AT_THREADS, BwdSmem::TOTAL, st>>>(tm_qkv, tm_do, p);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
+    attn_bwd_kernel<false><<<grid, AT_THREADS, BwdSmem::TOTAL, st>>>(tm_qkv, tm_do, p);
+  }
+  B200_CUDA(cudaGetLastError());
+  const long long rows = (long long)B * N;
+  attn_dq_convert_kernel<<<num_sms() * 4, 256, 0, st>>>((const float*)workspace, (__nv_bfloat16*)dqkv, rows, d);
+  B200_CUDA(cudaGetLastError());
+  return OK;
+}
+
+}  // extern "C"
