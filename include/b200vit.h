@@ -57,12 +57,15 @@ int b200vit_gemm_wgrad(const void* dy, const void* x, float* dw, int M, int N, i
  * qkv: [B, N, 3, H, 64] bf16 == the row-major output of the QKV Linear, "(qkv h d)" of transformer.py:27;
  * o: [B, N, H*64] bf16 == "b h n d -> b n (h d)" of transformer.py:29; lse: [B, H, N] fp32 (may be NULL).
  * Replaces F.scaled_dot_product_attention at transformer.py:28 (causal = additive -inf mask of
- * transformer.py:22-25) and the SDPA inside nn.MultiheadAttention (blocks.py:60).  dropout_p must be 0. */
-int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int causal, void* stream);
+ * transformer.py:22-25) and the SDPA inside nn.MultiheadAttention (blocks.py:60).  dropout_p must be 0.
+ * seq_first != 0: tensors are [N, B, ...] (the LND layout of blocks.py:270) instead of [B, N, ...]. */
+int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int causal, int seq_first,
+                           void* stream);
 size_t b200vit_flash_attn_bwd_workspace_size(int B, int N, int H);
 /* dqkv: [B, N, 3, H, 64] bf16 gradient of qkv given d_o [B, N, H*64] bf16 */
 int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B,
-                           int N, int H, int causal, void* workspace, size_t workspace_bytes, void* stream);
+                           int N, int H, int causal, int seq_first, void* workspace, size_t workspace_bytes,
+                           void* stream);
 
 /* ---- LayerNorm on the fp32 residual stream (F.layer_norm transformer.py:43-44; nn.LayerNorm blocks.py:43,48)
  * fwd: v = x (+ add_bf16) ; x_out = v (optional) ; y = LN(v) * gamma + beta -> bf16 and/or fp32 ; saves mean, rstd

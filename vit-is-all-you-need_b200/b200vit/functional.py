@@ -1,0 +1,288 @@
+"""torch.autograd.Functions that string the C-ABI kernels into the reference's blocks.
+
+The save-for-backward policy lives here.  Residual stream and parameters are fp32 (as in the reference under
+autocast); GEMM operands, attention I/O and saved activations are bf16; weight gradients are
+produced in fp32 by the wgrad GEMMs.
+"""
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+# ------------------------------------------------------------------------------------------------------------
+# bf16 operand cache for fp32 parameters (refreshed when the optimiser has touched the parameter)
+# ------------------------------------------------------------------------------------------------------------
+def bf16_of(p: torch.Tensor) -> torch.Tensor:
+    key = (p._version, p.data_ptr())
+    cached = getattr(p, "_b200_bf16", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    src = p.detach()
+    if src.dtype != F32:
+        src = src.float()
+    t = ops.cast_bf16(src.contiguous())
+    try:
+        p._b200_bf16 = (key, t)
+    except Exception:  # pragma: no cover  (tensors that refuse attributes)
+        pass
+    return t
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype != F32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _as_rows_f32(x):
+    x = x.detach()
+    if x.dtype != F32:
+        x = x.float()
+    return x.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# transformer.TransformerLayer (transformer.py:31-45): x + attn(LN(x)); x + mlp(LN(x)); affine-free LN, no out-proj
+# ------------------------------------------------------------------------------------------------------------
+class LayerParams:
+    __slots__ = ("qkv_w", "qkv_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")
+
+    def __init__(self, qkv_w, qkv_b, fc1_w, fc1_b, fc2_w, fc2_b):
+        self.qkv_w, self.qkv_b, self.fc1_w, self.fc1_b, self.fc2_w, self.fc2_b = qkv_w, qkv_b, fc1_w, fc1_b, fc2_w, fc2_b
+
+
+def layer_forward(x0, P: LayerParams, B, N, H, causal, save):
+    """x0: [B*N, d] fp32 contiguous.  Returns x2 [B*N, d] fp32 and (when save) the tensors backward needs."""
+    a, _, mean1, rstd1, _ = ops.layernorm_fwd(x0)
+    qkv = ops.gemm_bias(a, bf16_of(P.qkv_w), _f32c(P.qkv_b))
+    o, lse = ops.flash_attn_fwd(qkv, B, N, H, causal, want_lse=save)
+    b, _, mean2, rstd2, x1 = ops.layernorm_fwd(x0, add=o.view(B * N, -1), want_x_out=True)
+    g, u = ops.gemm_bias_gelu(b, bf16_of(P.fc1_w), _f32c(P.fc1_b), save_u=save)
+    x2 = ops.gemm_bias_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1)
+    saved = (x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g) if save else None
+    return x2, saved
+
+
+def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_dx=True):
+    """dx2: [B*N, d] fp32 (dx2_bf16: optional bf16 copy).  Returns (dx0, dx0_bf16, grads in LayerParams order)."""
+    x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g = saved
+    dv = dx2_bf16 if dx2_bf16 is not None else ops.cast_bf16(dx2)
+    d_fc2_w = ops.gemm_wgrad(dv, g)
+    d_fc2_b = ops.colsum_bf16(dv)
+    du = ops.gemm_dgrad_dgelu(dv, bf16_of(P.fc2_w), u)
+    d_fc1_w = ops.gemm_wgrad(du, b)
+    d_fc1_b = ops.colsum_bf16(du)
+    db = ops.gemm_dgrad(du, bf16_of(P.fc1_w))
+    dx1, dx1_bf16, _, _ = ops.layernorm_bwd(db, x1, mean2, rstd2, dres=dx2, want_bf16=True)
+    dqkv = ops.flash_attn_bwd(qkv, o, dx1_bf16.view(B, N, -1), lse, B, N, H, causal).view(B * N, -1)
+    d_qkv_w = ops.gemm_wgrad(dqkv, a)
+    d_qkv_b = ops.colsum_bf16(dqkv)
+    dx0 = dx0_bf16 = None
+    if need_dx:
+        da = ops.gemm_dgrad(dqkv, bf16_of(P.qkv_w))
+        dx0, dx0_bf16, _, _ = ops.layernorm_bwd(da, x0, mean1, rstd1, dres=dx1, want_bf16=True)
+    return dx0, dx0_bf16, (d_qkv_w, d_qkv_b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b)
+
+
+class TransformerStackFn(torch.autograd.Function):
+    """A stack of transformer.TransformerLayer (1 layer == TransformerLayer.forward, n == Transformer.forward,
+    transformer.py:52-54).  Keeping the stack in one node lets backward hand the bf16 copy of the residual
+    gradient from layer to layer without an extra cast pass."""
+
+    @staticmethod
+    def forward(ctx, x, n_heads, causal, *params):
+        B, N, d = x.shape
+        n_layers = len(params) // 6
+        layers = [LayerParams(*params[6 * i:6 * i + 6]) for i in range(n_layers)]
+        need_grad = any(ctx.needs_input_grad)  # grad mode is off inside forward(); this reflects the caller's
+        h = _as_rows_f32(x).view(B * N, d)
+        saved_all = []
+        for P in layers:
+            h, saved = layer_forward(h, P, B, N, n_heads, causal, need_grad)
+            saved_all.append(saved)
+        ctx.layers = layers
+        ctx.saved_all = saved_all
+        ctx.dims = (B, N, d, n_heads, causal)
+        ctx.x_needs_grad = x.requires_grad
+        return h.view(B, N, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, N, d, H, causal = ctx.dims
+        dx = _as_rows_f32(dy).view(B * N, d)
+        dx_bf16 = None
+        grads = []
+        n = len(ctx.layers)
+        for i in range(n - 1, -1, -1):
+            need_dx = i > 0 or ctx.x_needs_grad
+            dx, dx_bf16, g = layer_backward(dx, dx_bf16, ctx.saved_all[i], ctx.layers[i], B, N, H, causal, need_dx)
+            ctx.saved_all[i] = None  # free activations as we go
+            grads.append(g)
+        flat = []
+        for g in reversed(grads):
+            flat.extend(g)
+        ctx.saved_all = None
+        return (dx.view(B, N, d) if dx is not None else None, None, None, *flat)
+
+
+class AttentionFn(torch.autograd.Function):
+    """transformer.Attention.forward on its own (transformer.py:26-29): qkv Linear + SDPA, no out-proj."""
+
+    @staticmethod
+    def forward(ctx, x, qkv_w, qkv_b, n_heads, causal):
+        B, N, d = x.shape
+        a = ops.cast_bf16(_as_rows_f32(x).view(B * N, d))
+        qkv = ops.gemm_bias(a, bf16_of(qkv_w), _f32c(qkv_b))
+        o, lse = ops.flash_attn_fwd(qkv, B, N, n_heads, causal)
+        ctx.saved = (a, qkv, o, lse, qkv_w)
+        ctx.dims = (B, N, d, n_heads, causal)
+        return o.float()
+
+    @staticmethod
+    def backward(ctx, do):
+        a, qkv, o, lse, qkv_w = ctx.saved
+        B, N, d, H, causal = ctx.dims
+        do16 = ops.cast_bf16(_as_rows_f32(do).view(B * N, d)).view(B, N, d)
+        dqkv = ops.flash_attn_bwd(qkv, o, do16, lse, B, N, H, causal).view(B * N, -1)
+        dw = ops.gemm_wgrad(dqkv, a)
+        db = ops.colsum_bf16(dqkv)
+        dx = ops.gemm_dgrad(dqkv, bf16_of(qkv_w)).float().view(B, N, d)
+        return dx, dw, db, None, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Patch embedding of ViT (train_vit.py:34-36,38-45; blocks.py:235-237,257-267)
+# ------------------------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, pos_emb, extra_emb, patch):
+        B, C, H, W = x.shape
+        d = conv_w.shape[0]
+        extra = 0 if extra_emb is None else extra_emb.shape[0]
+        w16 = bf16_of(conv_w).view(d, -1)
+        tokens, cols = ops.patch_embed_fwd(_as_rows_f32(x), w16, _f32c(conv_b), _f32c(pos_emb),
+                                           _f32c(extra_emb) if extra > 0 else None, patch)
+        ctx.saved = (cols, conv_w)
+        ctx.dims = (B, C, H, W, patch, d, extra)
+        ctx.x_needs_grad = x.requires_grad
+        ctx.has_bias = conv_b is not None
+        ctx.has_extra = extra_emb is not None
+        return tokens
+
+    @staticmethod
+    def backward(ctx, dtokens):
+        cols, conv_w = ctx.saved
+        B, C, H, W, p, d, extra = ctx.dims
+        dsum, dpe = ops.patch_embed_bwd_reduce(_as_rows_f32(dtokens), extra)
+        dW = ops.gemm_wgrad(dpe, cols).view(conv_w.shape)
+        dpos = dsum[extra:]
+        db = ops.colsum_f32(dpos.contiguous()) if ctx.has_bias else None
+        dextra = dsum[:extra] if ctx.has_extra else None
+        dx = None
+        if ctx.x_needs_grad:
+            dcols = ops.gemm_dgrad(dpe, bf16_of(conv_w).view(d, -1))
+            dx = ops.col2im(dcols, B, C, H, W, p)
+        return dx, dW, db, dpos, dextra, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# blocks.ResidualAttentionBlock (blocks.py:32-70): affine LN, MHA (in_proj + out_proj), [L, B, d] layout
+# ------------------------------------------------------------------------------------------------------------
+class ResidualAttentionBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n_heads, has_mlp, ln1_w, ln1_b, in_w, in_b, out_w, out_b, *mlp):
+        L, B, d = x.shape
+        M = L * B
+        x0 = _as_rows_f32(x).view(M, d)
+        a, _, mean1, rstd1, _ = ops.layernorm_fwd(x0, gamma=_f32c(ln1_w), beta=_f32c(ln1_b))
+        qkv = ops.gemm_bias(a, bf16_of(in_w), _f32c(in_b))
+        o, lse = ops.flash_attn_fwd(qkv, B, L, n_heads, False, seq_first=True)
+        o2 = o.view(M, d)
+        x1 = ops.gemm_bias_residual(o2, bf16_of(out_w), _f32c(out_b), x0)
+        saved = [x0, mean1, rstd1, a, qkv, o, lse, x1]
+        y = x1
+        if has_mlp:
+            ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b = mlp
+            b, _, mean2, rstd2, _ = ops.layernorm_fwd(x1, gamma=_f32c(ln2_w), beta=_f32c(ln2_b))
+            g, u = ops.gemm_bias_gelu(b, bf16_of(fc_w), _f32c(fc_b))
+            y = ops.gemm_bias_residual(g, bf16_of(proj_w), _f32c(proj_b), x1)
+            saved += [mean2, rstd2, b, u, g]
+        ctx.saved = saved
+        ctx.params = (ln1_w, in_w, out_w) + tuple(mlp)
+        ctx.dims = (L, B, d, n_heads, has_mlp)
+        return y.view(L, B, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L, B, d, H, has_mlp = ctx.dims
+        M = L * B
+        s = ctx.saved
+        x0, mean1, rstd1, a, qkv, o, lse, x1 = s[:8]
+        ln1_w, in_w, out_w = ctx.params[:3]
+        dx2 = _as_rows_f32(dy).view(M, d)
+        mlp_grads = ()
+        if has_mlp:
+            mean2, rstd2, b, u, g = s[8:]
+            ln2_w, _, fc_w, _, proj_w, _ = ctx.params[3:]
+            dv = ops.cast_bf16(dx2)
+            d_proj_w = ops.gemm_wgrad(dv, g)
+            d_proj_b = ops.colsum_bf16(dv)
+            du = ops.gemm_dgrad_dgelu(dv, bf16_of(proj_w), u)
+            d_fc_w = ops.gemm_wgrad(du, b)
+            d_fc_b = ops.colsum_bf16(du)
+            db = ops.gemm_dgrad(du, bf16_of(fc_w))
+            dx1, dx1_16, d_ln2_w, d_ln2_b = ops.layernorm_bwd(db, x1, mean2, rstd2, gamma=_f32c(ln2_w), dres=dx2,
+                                                              want_bf16=True, affine_grads=True)
+            mlp_grads = (d_ln2_w, d_ln2_b, d_fc_w, d_fc_b, d_proj_w, d_proj_b)
+        else:
+            dx1, dx1_16 = dx2, ops.cast_bf16(dx2)
+        d_out_w = ops.gemm_wgrad(dx1_16, o.view(M, d))
+        d_out_b = ops.colsum_bf16(dx1_16)
+        do = ops.gemm_dgrad(dx1_16, bf16_of(out_w))
+        dqkv = ops.flash_attn_bwd(qkv, o, do.view(L, B, d), lse, B, L, H, False, seq_first=True).view(M, -1)
+        d_in_w = ops.gemm_wgrad(dqkv, a)
+        d_in_b = ops.colsum_bf16(dqkv)
+        da = ops.gemm_dgrad(dqkv, bf16_of(in_w))
+        dx0, _, d_ln1_w, d_ln1_b = ops.layernorm_bwd(da, x0, mean1, rstd1, gamma=_f32c(ln1_w), dres=dx1,
+                                                     want_bf16=False, affine_grads=True)
+        ctx.saved = None
+        return (dx0.view(L, B, d), None, None, d_ln1_w, d_ln1_b, d_in_w, d_in_b, d_out_w, d_out_b, *mlp_grads)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# VQ lookups: train_titok.Quantizer (train_titok.py:45-59) and blocks.VectorQuantizer (blocks.py:405-505)
+# ------------------------------------------------------------------------------------------------------------
+class VQFn(torch.autograd.Function):
+    """Returns (quantized, indices, mse, commitment_cost*mse, (1+cc)*mse).  `gather_normalized`/`channels_first`
+    select the blocks.py flavour.  Gradients: straight-through to x plus the two MSE terms."""
+
+    @staticmethod
+    def forward(ctx, x, codebook, l2, gather_normalized, channels_first, commitment_cost):
+        xf = _as_rows_f32(x)
+        cb = _f32c(codebook)
+        q, idx, losses = ops.vq_fwd(xf, cb, l2=l2, gather_normalized=gather_normalized,
+                                    channels_first=channels_first, commitment_cost=commitment_cost)
+        ctx.saved = (xf, cb, idx)
+        ctx.cfg = (l2, gather_normalized, channels_first, commitment_cost)
+        ctx.mark_non_differentiable(idx)
+        return q, idx, losses[0], losses[1], losses[2]
+
+    @staticmethod
+    def backward(ctx, dq, _didx, d_mse, d_commit, d_total):
+        xf, cb, idx = ctx.saved
+        l2, gn, cf, cc = ctx.cfg
+        # d/d(codebook_loss = mse) -> code rows ; d/d(commitment = cc*mse) -> x ; total = both
+        zero = torch.zeros((), device=xf.device, dtype=F32)
+        d_mse = zero if d_mse is None else d_mse.float()
+        d_commit = zero if d_commit is None else d_commit.float()
+        d_total = zero if d_total is None else d_total.float()
+        coef = torch.stack([cc * (d_commit + d_total), d_mse + d_total]).contiguous()
+        gq = torch.zeros_like(xf) if dq is None else _as_rows_f32(dq)
+        dx, dC = ops.vq_bwd(xf, cb, idx, gq, coef, l2=l2, gather_normalized=gn, channels_first=cf)
+        return dx, dC, None, None, None, None

@@ -1,0 +1,244 @@
+"""Drop-in nn.Modules with the reference's constructors, forward signatures, attributes and state_dict keys.
+
+    transformer.py:5-59   TransformerConfig, Attention, TransformerLayer, Transformer, S, B, L, transformer_configs
+    train_vit.py:16-53    ViTConfig, ViT, ViTClassifier
+    train_titok.py:45-59  Quantizer
+    blocks.py:32-70       ResidualAttentionBlock
+    blocks.py:405-505     VectorQuantizer
+
+Parameters stay ordinary fp32 nn.Parameters (AdamW / GradScaler / clip_grad_norm_ / torch.save work unchanged);
+all arithmetic on the hot path runs in the hand-written sm_100a kernels behind the C ABI.  There is no CPU or
+eager-PyTorch fallback: CPU tensors raise.
+"""
+from collections import OrderedDict
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+
+
+# ------------------------------------------------------------------------------------------------ transformer.py
+@dataclass
+class TransformerConfig:
+    n_layers: int
+    n_heads: int
+    n_embd: int
+    block_size: int
+    causal: bool = False
+    dropout: float = 0.0
+
+    def __post_init__(self):
+        self.head_dim = self.n_embd // self.n_heads
+
+
+def _copy_config(module, config):
+    if "causal" not in config.__dict__:
+        config.causal = False  # same backwards-compat hack as transformer.py:19
+    for k, v in config.__dict__.items():
+        setattr(module, k, v)
+
+
+def _check_supported(module):
+    if module.head_dim != 64:
+        raise NotImplementedError(f"b200vit attention kernels are built for head_dim 64 (got {module.head_dim}); "
+                                  "every shipped reference config uses 64 (transformer.py:56-58)")
+    if module.dropout != 0.0:
+        raise NotImplementedError("b200vit: dropout > 0 is not implemented on the fused path yet (parity is only "
+                                  "defined at dropout = 0, SURVEY.md §0.6); construct the config with dropout=0.0")
+
+
+class Attention(nn.Module):
+    """transformer.Attention (transformer.py:16-29): fused QKV Linear + SDPA, no output projection."""
+
+    def __init__(self, config: TransformerConfig):
+        super().__init__()
+        _copy_config(self, config)
+        self.qkv = nn.Linear(self.n_embd, self.n_embd * 3)
+        if self.causal:
+            # kept only so that state_dict() carries the same `mask` key/shape as the reference
+            mask = torch.triu(torch.ones(config.block_size, config.block_size), diagonal=1)
+            mask = mask.masked_fill(mask == 1, float("-inf"))
+            self.register_buffer("mask", mask)
+        _check_supported(self)
+
+    def forward(self, x):
+        return Fn.AttentionFn.apply(x, self.qkv.weight, self.qkv.bias, self.n_heads, bool(self.causal))
+
+
+class TransformerLayer(nn.Module):
+    """transformer.TransformerLayer (transformer.py:31-45)."""
+
+    def __init__(self, config: TransformerConfig):
+        super().__init__()
+        _copy_config(self, config)
+        self.multi_attn = Attention(config)
+        self.mlp = nn.Sequential(
+            nn.Linear(self.n_embd, 4 * self.n_embd),
+            nn.GELU(),
+            nn.Linear(4 * self.n_embd, self.n_embd),
+            nn.Dropout(self.dropout),
+        )
+
+    def _params(self):
+        return (self.multi_attn.qkv.weight, self.multi_attn.qkv.bias, self.mlp[0].weight, self.mlp[0].bias,
+                self.mlp[2].weight, self.mlp[2].bias)
+
+    def forward(self, x):
+        return Fn.TransformerStackFn.apply(x, self.n_heads, bool(self.causal), *self._params())
+
+
+class Transformer(nn.Module):
+    """transformer.Transformer (transformer.py:47-54): layer stack, no final norm."""
+
+    def __init__(self, config: TransformerConfig):
+        super().__init__()
+        _copy_config(self, config)
+        self.layers = nn.ModuleList([TransformerLayer(config) for _ in range(config.n_layers)])
+
+    def forward(self, x):
+        params = []
+        for layer in self.layers:
+            params.extend(layer._params())
+        return Fn.TransformerStackFn.apply(x, self.n_heads, bool(self.causal), *params)
+
+
+def S(**kwargs): return TransformerConfig(n_layers=6, n_heads=8, n_embd=512, **kwargs)
+def B(**kwargs): return TransformerConfig(n_layers=12, n_heads=12, n_embd=768, **kwargs)
+def L(**kwargs): return TransformerConfig(n_layers=24, n_heads=16, n_embd=1024, **kwargs)
+
+
+transformer_configs = {"S": S, "B": B, "L": L}
+
+
+# ------------------------------------------------------------------------------------------------ train_vit.py
+@dataclass
+class ViTConfig:
+    image_size: int
+    in_channels: int
+    patch_size: int
+    transformer: str
+    extra_tokens: int
+    dropout: float
+
+    def __post_init__(self):
+        self.n_patches = (self.image_size // self.patch_size) ** 2
+        self.patch_dim = 3 * self.patch_size ** 2
+        self.trans_config = transformer_configs[self.transformer](block_size=self.n_patches + self.extra_tokens,
+                                                                   dropout=self.dropout)
+
+
+class ViT(nn.Module):
+    """train_vit.ViT (train_vit.py:30-45): patchify conv + pos_emb + prepended extra tokens + Transformer."""
+
+    def __init__(self, args: ViTConfig):
+        super().__init__()
+        self.config = args
+        self.patch_proj = nn.Conv2d(in_channels=args.in_channels, out_channels=args.trans_config.n_embd,
+                                    kernel_size=args.patch_size, stride=args.patch_size)
+        self.pos_emb = nn.Embedding(args.n_patches, args.trans_config.n_embd)
+        self.extra_emb = nn.Embedding(args.extra_tokens, args.trans_config.n_embd)
+        self.transformer = Transformer(args.trans_config)
+
+    def forward(self, x):
+        extra = self.extra_emb.weight if self.config.extra_tokens > 0 else None
+        emb = Fn.PatchEmbedFn.apply(x, self.patch_proj.weight, self.patch_proj.bias,
+                                    self.pos_emb.weight[: self.config.n_patches], extra, self.config.patch_size)
+        return self.transformer(emb)
+
+
+class ViTClassifier(nn.Module):
+    """train_vit.ViTClassifier (train_vit.py:47-53); the head stays a plain nn.Linear (SURVEY.md §8f "next")."""
+
+    def __init__(self, vit_config: ViTConfig, num_classes=1000):
+        super().__init__()
+        self.vit = ViT(vit_config)
+        self.head = nn.Linear(vit_config.trans_config.n_embd, num_classes)
+
+    def forward(self, x):
+        return self.head(self.vit(x)[:, 0])
+
+
+# ------------------------------------------------------------------------------------------------ train_titok.py
+class Quantizer(nn.Module):
+    """train_titok.Quantizer (train_titok.py:45-59 == train_vit_vqgan.py:45-59): indices from l2-normalised
+    latents/codes, RAW codebook rows gathered, codebook + 0.25 commitment loss, straight-through output."""
+
+    def __init__(self, titok_config):
+        super().__init__()
+        self.codebook = nn.Embedding(titok_config.codebook_size, titok_config.latent_dim)
+        self.codebook.weight.data.uniform_(-1.0 / titok_config.codebook_size, 1.0 / titok_config.codebook_size)
+
+    def forward(self, x):
+        quantized, indices, _mse, _commit, total = Fn.VQFn.apply(x, self.codebook.weight, True, False, False, 0.25)
+        return quantized, indices.view(x.shape[:-1]), total
+
+
+# ------------------------------------------------------------------------------------------------ blocks.py
+class ResidualAttentionBlock(nn.Module):
+    """blocks.ResidualAttentionBlock (blocks.py:32-70); x is sequence-first [L, B, d]."""
+
+    def __init__(self, d_model, n_head, mlp_ratio=4.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        if act_layer is not nn.GELU or norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("b200vit ResidualAttentionBlock implements nn.GELU + nn.LayerNorm only")
+        if d_model // n_head != 64:
+            raise NotImplementedError("b200vit attention kernels are built for head_dim 64")
+        self.n_head = n_head
+        self.ln_1 = norm_layer(d_model)
+        self.attn = nn.MultiheadAttention(d_model, n_head)  # parameter container: in_proj_*, out_proj.*
+        self.mlp_ratio = mlp_ratio
+        if mlp_ratio > 0:
+            self.ln_2 = norm_layer(d_model)
+            mlp_width = int(d_model * mlp_ratio)
+            self.mlp = nn.Sequential(OrderedDict([
+                ("c_fc", nn.Linear(d_model, mlp_width)),
+                ("gelu", act_layer()),
+                ("c_proj", nn.Linear(mlp_width, d_model)),
+            ]))
+
+    def forward(self, x):
+        mlp = ()
+        if self.mlp_ratio > 0:
+            mlp = (self.ln_2.weight, self.ln_2.bias, self.mlp.c_fc.weight, self.mlp.c_fc.bias,
+                   self.mlp.c_proj.weight, self.mlp.c_proj.bias)
+        return Fn.ResidualAttentionBlockFn.apply(x, self.n_head, self.mlp_ratio > 0, self.ln_1.weight, self.ln_1.bias,
+                                                 self.attn.in_proj_weight, self.attn.in_proj_bias,
+                                                 self.attn.out_proj.weight, self.attn.out_proj.bias, *mlp)
+
+
+class VectorQuantizer(nn.Module):
+    """blocks.VectorQuantizer (blocks.py:405-505).  The clustering_vq branch is dead code in the reference
+    (undefined `gather`, blocks.py:457) and is rejected here."""
+
+    def __init__(self, codebook_size: int = 1024, token_size: int = 256, commitment_cost: float = 0.25,
+                 use_l2_norm: bool = False, clustering_vq: bool = False):
+        super().__init__()
+        if clustering_vq:
+            raise NotImplementedError("clustering_vq is broken in the reference (blocks.py:457) and not implemented")
+        self.codebook_size = codebook_size
+        self.token_size = token_size
+        self.commitment_cost = commitment_cost
+        self.embedding = nn.Embedding(codebook_size, token_size)
+        self.embedding.weight.data.uniform_(-1.0 / codebook_size, 1.0 / codebook_size)
+        self.use_l2_norm = use_l2_norm
+        self.clustering_vq = clustering_vq
+
+    def forward(self, z):
+        z_q, idx, mse, commit, total = Fn.VQFn.apply(z, self.embedding.weight, self.use_l2_norm, self.use_l2_norm,
+                                                     True, float(self.commitment_cost))
+        result = dict(quantizer_loss=total, commitment_loss=commit, codebook_loss=mse,
+                      min_encoding_indices=idx.view(z.shape[0], z.shape[2], z.shape[3]))
+        return z_q, result
+
+    def get_codebook_entry(self, indices):
+        if len(indices.shape) == 1:
+            z_quantized = self.embedding(indices)
+        elif len(indices.shape) == 2:
+            z_quantized = torch.einsum("bd,dn->bn", indices, self.embedding.weight)
+        else:
+            raise NotImplementedError
+        if self.use_l2_norm:
+            z_quantized = torch.nn.functional.normalize(z_quantized, dim=-1)
+        return z_quantized

@@ -95,21 +95,21 @@ def gemm_wgrad(dy, x, out=None, accumulate=False):
 
 
 # ---------------------------------------------------------------- attention
-def flash_attn_fwd(qkv, B, N, H, causal=False, want_lse=True):
+def flash_attn_fwd(qkv, B, N, H, causal=False, want_lse=True, seq_first=False):
     d = H * 64
     assert qkv.numel() == B * N * 3 * d
-    o = torch.empty(B, N, d, device=qkv.device, dtype=BF16)
+    o = torch.empty((N, B, d) if seq_first else (B, N, d), device=qkv.device, dtype=BF16)
     lse = torch.empty(B, H, N, device=qkv.device, dtype=F32) if want_lse else None
-    _call("b200vit_flash_attn_fwd", qkv, ptr(_chk(qkv, BF16, "qkv")), ptr(o), ptr(lse), B, N, H, 1 if causal else 0, stream_ptr())
+    _call("b200vit_flash_attn_fwd", qkv, ptr(_chk(qkv, BF16, "qkv")), ptr(o), ptr(lse), B, N, H, 1 if causal else 0, 1 if seq_first else 0, stream_ptr())
     return o, lse
 
 
-def flash_attn_bwd(qkv, o, d_o, lse, B, N, H, causal=False):
+def flash_attn_bwd(qkv, o, d_o, lse, B, N, H, causal=False, seq_first=False):
     d = H * 64
-    dqkv = torch.empty(B, N, 3 * d, device=qkv.device, dtype=BF16)
+    dqkv = torch.empty((N, B, 3 * d) if seq_first else (B, N, 3 * d), device=qkv.device, dtype=BF16)
     ws = torch.empty(B * N * d, device=qkv.device, dtype=F32)
     _call("b200vit_flash_attn_bwd", qkv, ptr(_chk(qkv, BF16, "qkv")), ptr(_chk(o, BF16, "o")), ptr(_chk(d_o, BF16, "d_o")), ptr(_chk(lse, F32, "lse")),
-          ptr(dqkv), B, N, H, 1 if causal else 0, ptr(ws), ws.numel() * 4, stream_ptr())
+          ptr(dqkv), B, N, H, 1 if causal else 0, 1 if seq_first else 0, ptr(ws), ws.numel() * 4, stream_ptr())
     return dqkv
 
 

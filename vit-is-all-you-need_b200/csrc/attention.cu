@@ -30,6 +30,7 @@ constexpr float LN2 = 0.6931471805599453f;
 
 struct AttnParams {
   int B, N, H, d;
+  long long sb, sn;     // token (b, n) lives at row b*sb + n*sn  ([B,N,..]: N,1 ; sequence-first [N,B,..]: 1,B)
   int causal;
   float scale;          // 1/sqrt(64)
   float scale_log2e;    // scale * log2(e)
@@ -244,7 +245,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
     }
     if (q < p.N) {
       const float inv = 1.0f / l;
-      __nv_bfloat16* orow = p.o + ((long long)b * p.N + q) * p.d + hh * AT_HD;
+      __nv_bfloat16* orow = p.o + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         uint4 w;
@@ -382,8 +383,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       float lse2 = 0.f, Dq = 0.f;
       if (qv) {
         lse2 = p.lse[((long long)b * p.H + hh) * p.N + q] * LOG2E;
-        const uint4* orow = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.N + q) * p.d + hh * AT_HD);
-        const uint4* drow = reinterpret_cast<const uint4*>(p.do_in + ((long long)b * p.N + q) * p.d + hh * AT_HD);
+        const uint4* orow = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD);
+        const uint4* drow = reinterpret_cast<const uint4*>(p.do_in + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint4 a = orow[c], g = drow[c];
@@ -430,7 +431,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         tmem_ld32(tmem_dQ + lane_off + c * 32, v);
         tmem_ld_wait();
         if (qv) {
-          float* dst = p.dq_acc + ((long long)b * p.N + q) * p.d + hh * AT_HD + c * 32;
+          float* dst = p.dq_acc + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
             atomicAdd(reinterpret_cast<float4*>(dst + i),
@@ -452,7 +453,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_off + c * 32, v);
         tmem_ld_wait();
         if (key < p.N) {
-          __nv_bfloat16* dst = p.dqkv + ((long long)b * p.N + key) * 3 * p.d + (which + 1) * p.d + hh * AT_HD + c * 32;
+          __nv_bfloat16* dst = p.dqkv + ((long long)b * p.sb + key * p.sn) * 3 * p.d + (which + 1) * p.d + hh * AT_HD + c * 32;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 w;
@@ -486,9 +487,10 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloa
   }
 }
 
-static int make_tmap_bnd(CUtensorMap* tm, const void* base, int B, int N, int row_elems) {
+static int make_tmap_bnd(CUtensorMap* tm, const void* base, int B, int N, int row_elems, int seq_first) {
   const uint64_t dims[3] = {(uint64_t)row_elems, (uint64_t)N, (uint64_t)B};
-  const uint64_t strides[3] = {2, (uint64_t)row_elems * 2, (uint64_t)N * row_elems * 2};
+  const uint64_t sn = seq_first ? (uint64_t)B : 1, sb = seq_first ? 1 : (uint64_t)N;
+  const uint64_t strides[3] = {2, sn * row_elems * 2, sb * row_elems * 2};
   const uint32_t box[3] = {64, 128, 1};
   return make_tmap_nd_bf16(tm, base, 3, dims, strides, box, true);
 }
@@ -500,15 +502,16 @@ using namespace b200;
 extern "C" {
 
 int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int causal,
-                           void* stream) {
+                           int seq_first, void* stream) {
   B200_REQUIRE(qkv && o, "flash_attn_fwd: null pointer");
   B200_REQUIRE(B > 0 && N > 0 && H > 0, "flash_attn_fwd: bad sizes");
   const int d = H * AT_HD;
   CUtensorMap tm;
-  int rc = make_tmap_bnd(&tm, qkv, B, N, 3 * d);
+  int rc = make_tmap_bnd(&tm, qkv, B, N, 3 * d, seq_first);
   if (rc != OK) return rc;
   AttnParams p{};
   p.B = B; p.N = N; p.H = H; p.d = d; p.causal = causal;
+  p.sb = seq_first ? 1 : N; p.sn = seq_first ? B : 1;
   p.scale = 0.125f; p.scale_log2e = 0.125f * LOG2E;
   p.o = (__nv_bfloat16*)o; p.lse = lse;
   dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
@@ -529,19 +532,20 @@ size_t b200vit_flash_attn_bwd_workspace_size(int B, int N, int H) {
 }
 
 int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
-                           int B, int N, int H, int causal, void* workspace, size_t workspace_bytes,
-                           void* stream) {
+                           int B, int N, int H, int causal, int seq_first, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   B200_REQUIRE(qkv && o && d_o && lse && dqkv && workspace, "flash_attn_bwd: null pointer");
   B200_REQUIRE(workspace_bytes >= b200vit_flash_attn_bwd_workspace_size(B, N, H), "flash_attn_bwd: workspace too small");
   const int d = H * AT_HD;
   CUtensorMap tm_qkv, tm_do;
-  int rc = make_tmap_bnd(&tm_qkv, qkv, B, N, 3 * d);
+  int rc = make_tmap_bnd(&tm_qkv, qkv, B, N, 3 * d, seq_first);
   if (rc != OK) return rc;
-  rc = make_tmap_bnd(&tm_do, d_o, B, N, d);
+  rc = make_tmap_bnd(&tm_do, d_o, B, N, d, seq_first);
   if (rc != OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   AttnParams p{};
   p.B = B; p.N = N; p.H = H; p.d = d; p.causal = causal;
+  p.sb = seq_first ? 1 : N; p.sn = seq_first ? B : 1;
   p.scale = 0.125f; p.scale_log2e = 0.125f * LOG2E;
   p.lse = const_cast<float*>(lse);
   p.o_in = (const __nv_bfloat16*)o; p.do_in = (const __nv_bfloat16*)d_o;
