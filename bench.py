@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""ViT-B/16 224px bf16 training throughput on 1..8 B200s (BASELINE.json configs[1]) through the drop-in modules.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]        # our arm
+    python bench.py --impl reference ...                                    # the reference's CPU path (oracle port)
+
+One "step" = forward + cross-entropy + backward + AdamW on a per-GPU batch of synthetic images (weak scaling).
+`value` is measured with the inputs already resident in HBM; `e2e` runs the same step from pinned HOST buffers
+(images + labels copied host->device and the loss read back device->host inside the timed region, every step).
+Prints ONE JSON line on rank 0.  See DESIGN.md §Measurement for the roofline arithmetic.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "vit-is-all-you-need_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "vit_b16_224_train_images_per_sec"
+UNIT = "images/s"
+IMAGE, PATCH, CLASSES = 224, 16, 1000
+D, LAYERS, HEADS, NTOK = 768, 12, 12, 197
+
+
+def train_flops_per_image():
+    """3 x (layers x F_layer + F_head) + 2 x F_patch, 2mnk per GEMM, no recompute counted."""
+    f_layer = 2 * NTOK * D * 3 * D + 4 * NTOK * NTOK * D + 16 * NTOK * D * D
+    f_patch = 2 * (NTOK - 1) * (3 * PATCH * PATCH) * D
+    f_head = 2 * D * CLASSES
+    return 3 * (LAYERS * f_layer + f_head) + 2 * f_patch
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"bf16_tflops": p.get("bf16_tflops"), "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p.get("hbm_gbs"), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def numpy_vit_b_params(rng):
+    import numpy as np
+
+    def w(*s):
+        return (rng.standard_normal(s) * 0.02).astype(np.float32)
+    layers = [{"qkv_w": w(3 * D, D), "qkv_b": w(3 * D), "fc1_w": w(4 * D, D), "fc1_b": w(4 * D),
+               "fc2_w": w(D, 4 * D), "fc2_b": w(D)} for _ in range(LAYERS)]
+    return {"conv_w": w(D, 3, PATCH, PATCH), "conv_b": w(D), "pos_emb": w(NTOK - 1, D), "extra_emb": w(1, D),
+            "layers": layers, "head_w": w(CLASSES, D), "head_b": w(CLASSES)}
+
+
+def cpu_reference_step_rate(batch, steps, warmup):
+    """The reference's CPU implementation of the path == the numpy oracle port (fwd + CE + bwd, fp32, all host
+    threads through the BLAS numpy links).  Returns (images/s, seconds per step)."""
+    import numpy as np
+    from oracle import vit_oracle as O
+    rng = np.random.default_rng(0)
+    P = numpy_vit_b_params(rng)
+    x = rng.standard_normal((batch, 3, IMAGE, IMAGE)).astype(np.float32)
+    labels = rng.integers(0, CLASSES, size=(batch,))
+    for _ in range(warmup):
+        O.vit_classifier_loss_and_grads(x, labels, P, HEADS)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.vit_classifier_loss_and_grads(x, labels, P, HEADS)
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    batch = args.cpu_batch
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    ips, dt = cpu_reference_step_rate(batch, steps, warm)
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 224px train step (fwd+CE+bwd), reference CPU path (numpy oracle port)",
+                   "global_batch": batch, "parallelism": "cpu"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{steps} step(s) of batch {batch} (ViT-B/16 224, fwd+CE+bwd, fp32 numpy/BLAS)"},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_model(torch, M, device):
+    torch.manual_seed(0)
+    cfg = M.ViTConfig(IMAGE, 3, PATCH, "B", 1, 0.0)
+    model = M.ViTClassifier(cfg, num_classes=CLASSES).to(device)
+    return model
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from b200vit import ddp as b200_ddp
+    from b200vit import modules as M
+    from b200vit import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    B = args.batch
+    model = build_model(torch, M, device)
+    wrapped = b200_ddp.DataParallel(model, bucket_mb=args.bucket_mb) if world > 1 else model
+    optim = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2, fused=True)
+    loss_fn = torch.nn.CrossEntropyLoss()
+
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    n_host = 2
+    host_images = [torch.randn(B, 3, IMAGE, IMAGE, generator=g).pin_memory() for _ in range(n_host)]
+    host_labels = [torch.randint(0, CLASSES, (B,), generator=g).pin_memory() for _ in range(n_host)]
+    dev_images = [h.to(device) for h in host_images]
+    dev_labels = [h.to(device) for h in host_labels]
+
+    def step(images, labels):
+        optim.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            pred = wrapped(images)
+            loss = loss_fn(pred.float(), labels)
+        loss.backward()
+        optim.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident arm
+    def dev_step(i):
+        step(dev_images[i % n_host], dev_labels[i % n_host])
+
+    for i in range(max(args.warmup, 3)):
+        dev_step(i)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ops.launch_count = 0
+    ms = timed(dev_step, args.steps)
+    launches = ops.launch_count
+    clk = clocks.stop() if rank == 0 else None
+    ips = world * B * args.steps / (ms / 1e3)
+
+    # ---- end-to-end arm: pinned host buffers, H2D prefetch on a copy stream, loss read back every step
+    copy_stream = torch.cuda.Stream(device=device)
+    state = {}
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            im = host_images[i % n_host].to(device, non_blocking=True)
+            lb = host_labels[i % n_host].to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        state["next"] = (im, lb, ev)
+
+    losses = []
+
+    def e2e_step(i):
+        if "next" not in state:
+            prefetch(i)
+        im, lb, ev = state.pop("next")
+        torch.cuda.current_stream().wait_event(ev)
+        im.record_stream(torch.cuda.current_stream()); lb.record_stream(torch.cuda.current_stream())
+        prefetch(i + 1)
+        loss = step(im, lb)
+        losses.append(loss.item())  # device -> host read of the step's result
+
+    for i in range(3):
+        e2e_step(i)
+    state.clear()
+    ms_e2e = timed(e2e_step, args.steps)
+    ips_e2e = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = B * 3 * IMAGE * IMAGE * 4 + B * 8
+    d2h = 4
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA-event timing over extra steps
+    peaks = load_peaks()
+    gemm_ms, gemm_flops, gemm_calls = ops.profile_gemms(lambda: dev_step(0), steps=2)
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+    step_tflops = ips / world * train_flops_per_image() / 1e12
+
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+
+    line = {
+        "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "ViT-B/16 224px ImageNet-shape train step (fwd + CE + bwd + AdamW), configs[1]",
+                   "per_gpu_batch": B, "global_batch": B * world, "seq_len": NTOK, "parallelism": f"dp{world}",
+                   "optimizer": "torch.optim.AdamW(fused=True)", "l2": "per-step working set >> 126 MB L2 (no flush needed)",
+                   "train_gflop_per_image": train_flops_per_image() / 1e9},
+        "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all Linear fwd/dgrad/wgrad launches of a step)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                     "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                     "traffic": None, "launches_timed": gemm_calls,
+                     "step_tflops_per_gpu": step_tflops, "step_frac_of_peak": step_tflops / peak if peak else None,
+                     "step_frac_of_nominal_2250": step_tflops / 2250.0},
+        "final_loss": losses[-1] if losses else None,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = args.cpu_batch
+        cips, cdt = cpu_reference_step_rate(cb, 1, 0)
+        line["cpu_baseline"] = {"value": cips, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"1 step of batch {cb} (ViT-B/16 224, fwd+CE+bwd, fp32 numpy oracle, {cdt:.1f} s)"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--bucket-mb", type=float, default=32.0)
+    ap.add_argument("--impl", type=str, default="b200vit", choices=["b200vit", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=4, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

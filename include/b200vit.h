@@ -34,9 +34,9 @@ int b200vit_debug_set(int key, int value); /* bring-up knobs (descriptor sweeps)
 /* y[M,N](bf16) = x[M,K] w[N,K]^T + bias[N]            nn.Linear forward, transformer.py:21,27 (qkv)   */
 int b200vit_gemm_bias(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
                       void* stream);
-/* u = x w^T + bias ; g(bf16) = GELU_erf(u) ; u(bf16) stored when u != NULL   transformer.py:37-38,
- * blocks.py:51-52 */
-int b200vit_gemm_bias_gelu(const void* x, const void* w, const float* bias, void* g, void* u, int M,
+/* u = x w^T + bias ; g(bf16) = GELU_erf(u) ; gprime(bf16) = GELU'(u) (saved for backward instead of u)
+ * transformer.py:37-38, blocks.py:51-52 */
+int b200vit_gemm_bias_gelu(const void* x, const void* w, const float* bias, void* g, void* gprime, int M,
                            int N, int K, void* stream);
 /* out[M,N](f32) = resid[M,N](f32) + x w^T + bias       transformer.py:39,44 ; blocks.py:53,67,69     */
 int b200vit_gemm_bias_residual(const void* x, const void* w, const float* bias, const float* resid,
@@ -46,8 +46,9 @@ int b200vit_gemm_bias_f32(const void* x, const void* w, const float* bias, float
                           int K, void* stream);
 /* dx[M,K](bf16) = dy[M,N] w[N,K]                       autograd of nn.Linear wrt input               */
 int b200vit_gemm_dgrad(const void* dy, const void* w, void* dx, int M, int N, int K, void* stream);
-/* dx[M,K](bf16) = (dy w) * GELU'(u[M,K])               autograd of Linear∘GELU, transformer.py:38-39 */
-int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* u, void* dx, int M, int N,
+/* dx[M,K](bf16) = (dy w) * gprime[M,K]                 autograd of Linear∘GELU, transformer.py:38-39;
+ * gprime = GELU'(u) as written by b200vit_gemm_bias_gelu */
+int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* gprime, void* dx, int M, int N,
                              int K, void* stream);
 /* dw[N,K](f32) (+)= dy[M,N]^T x[M,K]                   autograd of nn.Linear wrt weight              */
 int b200vit_gemm_wgrad(const void* dy, const void* x, float* dw, int M, int N, int K, int accumulate,

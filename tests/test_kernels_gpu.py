@@ -52,9 +52,9 @@ def test_gemm_forward_family(ops, M, N, K):
     ref = O.linear_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64))
     xd, wd, bd = to_dev(x, torch.bfloat16), to_dev(w, torch.bfloat16), to_dev(b)
     assert_close_bf16(ops.gemm_bias(xd, wd, bd), ref, "gemm_bias")
-    g, u = ops.gemm_bias_gelu(xd, wd, bd)
-    assert_close_bf16(u, ref, "gemm_bias_gelu.u")
-    assert_close_bf16(g, O.gelu_fwd(bf16_round(ref.astype(np.float32)).astype(np.float64)), "gemm_bias_gelu.g")
+    g, gp = ops.gemm_bias_gelu(xd, wd, bd)
+    assert_close_bf16(g, O.gelu_fwd(ref), "gemm_bias_gelu.g")
+    assert_close_bf16(gp, O.gelu_bwd(np.ones_like(ref), ref), "gemm_bias_gelu.gprime")
     out = ops.gemm_bias_residual(xd, wd, bd, to_dev(res))
     assert_close_bf16(out, ref + res, "gemm_bias_residual (fp32)", rel=2e-5)
     out = ops.gemm_bias_f32(xd, wd, None)
@@ -71,7 +71,7 @@ def test_gemm_dgrad_and_wgrad(ops, M, N, K):
     dx_ref, dw_ref, _ = O.linear_bwd(dy.astype(np.float64), x.astype(np.float64), w.astype(np.float64))
     dyd, xd, wd = to_dev(dy, torch.bfloat16), to_dev(x, torch.bfloat16), to_dev(w, torch.bfloat16)
     assert_close_bf16(ops.gemm_dgrad(dyd, wd), dx_ref, "gemm_dgrad")
-    assert_close_bf16(ops.gemm_dgrad_dgelu(dyd, wd, to_dev(u, torch.bfloat16)), O.gelu_bwd(dx_ref, u.astype(np.float64)), "gemm_dgrad_dgelu")
+    assert_close_bf16(ops.gemm_dgrad_dgelu(dyd, wd, to_dev(u, torch.bfloat16)), dx_ref * u.astype(np.float64), "gemm_dgrad_dgelu (x gprime)")
     dw = ops.gemm_wgrad(dyd, xd)
     assert_close_bf16(dw, dw_ref, "gemm_wgrad (fp32, split-K atomics)", rel=2e-5)
     dw2 = ops.gemm_wgrad(dyd, xd, out=dw.clone(), accumulate=True)

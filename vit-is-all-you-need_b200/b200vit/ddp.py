@@ -1,0 +1,170 @@
+"""Data-parallel training across the GPUs of one box: one process per GPU, parameters replicated, the batch
+sharded by rank, gradients averaged by a bucketed all-reduce (NCCL over NVLink 5 / NVSwitch) that overlaps the
+rest of backward.
+
+The reference is single-process (no torch.distributed anywhere); this layer is what §8(e) adds.
+
+Mechanics
+  * every trainable parameter owns a slot in a flat fp32 bucket (buckets are filled in reverse parameter order,
+    i.e. in the order backward produces gradients);
+  * the fused transformer backward asks `grad_slot(param)` for its slot and lets the wgrad GEMM / bias
+    reductions write straight into bucket memory, then calls `grad_ready(param)`;
+  * all other parameters (patch embedding, heads, codebooks ...) are copied into their slots from a
+    post-accumulate-grad hook;
+  * when the last slot of a bucket is ready an event is recorded on the compute stream and the bucket's
+    all-reduce is enqueued on a communication stream;
+  * an autograd end-of-backward callback waits for all buckets and points `param.grad` at the (averaged)
+    bucket views, so optimisers / GradScaler / clip_grad_norm_ run unchanged.
+Gradient accumulation over several backward passes is only supported inside `no_sync()`.
+"""
+import contextlib
+
+import torch
+import torch.distributed as dist
+
+from . import functional as Fn
+
+
+class _Bucket:
+    def __init__(self, numel, device, dtype):
+        self.flat = torch.zeros(numel, device=device, dtype=dtype)
+        self.params = []
+        self.pending = 0
+        self.work = None
+        self.ready = set()
+
+
+class DataParallel(torch.nn.Module):
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None):
+        super().__init__()
+        self.module = module
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.backend = dist.get_backend(process_group) if dist.is_initialized() else "none"
+        self._sync = True
+        self._in_backward = False
+        self._slots = {}
+        self.buckets = []
+        params = [p for p in module.parameters() if p.requires_grad]
+        if not params:
+            raise ValueError("DataParallel: module has no trainable parameters")
+        device, dtype = params[0].device, params[0].dtype
+        cap = int(bucket_mb * 1024 * 1024 / params[0].element_size())
+        groups, cur, cur_n = [], [], 0
+        for p in reversed(params):
+            if cur and cur_n + p.numel() > cap:
+                groups.append(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            groups.append(cur)
+        for g in groups:
+            b = _Bucket(sum(p.numel() for p in g), device, dtype)
+            off = 0
+            for p in g:
+                self._slots[p] = (b, b.flat[off:off + p.numel()].view(p.shape))
+                b.params.append(p)
+                off += p.numel()
+            self.buckets.append(b)
+        self.comm_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+        for p in params:
+            p.register_post_accumulate_grad_hook(self._hook)
+        self.broadcast_parameters()
+
+    # ---------------------------------------------------------------------------------------------- plumbing
+    def broadcast_parameters(self):
+        if self.world > 1:
+            for t in list(self.module.parameters()) + list(self.module.buffers()):
+                dist.broadcast(t.data, src=0, group=self.pg)
+
+    def forward(self, *args, **kwargs):
+        if self._sync and torch.is_grad_enabled():
+            Fn.set_grad_sink(self)
+        else:
+            Fn.set_grad_sink(None)
+        return self.module(*args, **kwargs)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        old, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = old
+
+    # ---------------------------------------------------------------------------------- gradient sink protocol
+    def grad_slot(self, param):
+        """Bucket view the producer may write this parameter's gradient into (None if unknown)."""
+        s = self._slots.get(param)
+        return None if s is None else s[1]
+
+    def grad_ready(self, param):
+        self._mark_ready(param)
+
+    def _hook(self, param):
+        if not self._sync:
+            return
+        b, view = self._slots[param]
+        if self._in_backward and param in b.ready:
+            return  # already delivered through the gradient sink (the bucket may be in flight)
+        if param.grad is not None and param.grad.data_ptr() != view.data_ptr():
+            view.copy_(param.grad)
+        self._mark_ready(param)
+
+    def _begin_backward(self):
+        self._in_backward = True
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.work = None
+            b.ready = set()
+        torch.autograd.Variable._execution_engine.queue_callback(self._finalize)
+
+    def _mark_ready(self, param):
+        if not self._sync:
+            return
+        if not self._in_backward:
+            self._begin_backward()
+        b, _ = self._slots[param]
+        if param in b.ready:
+            return
+        b.ready.add(param)
+        b.pending -= 1
+        if b.pending == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        if self.world == 1:
+            return
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self.comm_stream.wait_event(ev)
+                b.work = self._all_reduce(b.flat)
+        else:
+            b.work = self._all_reduce(b.flat)
+
+    def _all_reduce(self, flat):
+        if self.backend == "nccl":
+            return dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        work.wait()
+        flat.div_(self.world)
+        return None
+
+    def _finalize(self):
+        self._in_backward = False
+        for b in self.buckets:
+            if b.pending != 0:
+                # parameters that did not take part in this backward: reduce what is there (zeros for them)
+                for p in b.params:
+                    if p not in b.ready:
+                        self._slots[p][1].zero_()
+                self._launch(b)
+            if b.work is not None:
+                b.work.wait()  # compute stream waits for the NCCL stream
+                b.work = None
+        for p, (b, view) in self._slots.items():
+            if p in b.ready:
+                p.grad = view

@@ -31,6 +31,28 @@ def bf16_of(p: torch.Tensor) -> torch.Tensor:
     return t
 
 
+# ------------------------------------------------------------------------------------------------------------
+# Gradient sink (set by ddp.DataParallel): lets the wgrad kernels write straight into all-reduce buckets and
+# start a bucket's all-reduce while the rest of the fused backward is still running.
+# ------------------------------------------------------------------------------------------------------------
+_GRAD_SINK = None
+
+
+def set_grad_sink(sink):
+    global _GRAD_SINK
+    _GRAD_SINK = sink
+
+
+def _slot(param):
+    return None if _GRAD_SINK is None else _GRAD_SINK.grad_slot(param)
+
+
+def _ready(*params):
+    if _GRAD_SINK is not None:
+        for p in params:
+            _GRAD_SINK.grad_ready(p)
+
+
 def _f32c(t):
     if t is None:
         return None
@@ -63,7 +85,7 @@ def layer_forward(x0, P: LayerParams, B, N, H, causal, save):
     qkv = ops.gemm_bias(a, bf16_of(P.qkv_w), _f32c(P.qkv_b))
     o, lse = ops.flash_attn_fwd(qkv, B, N, H, causal, want_lse=save)
     b, _, mean2, rstd2, x1 = ops.layernorm_fwd(x0, add=o.view(B * N, -1), want_x_out=True)
-    g, u = ops.gemm_bias_gelu(b, bf16_of(P.fc1_w), _f32c(P.fc1_b), save_u=save)
+    g, u = ops.gemm_bias_gelu(b, bf16_of(P.fc1_w), _f32c(P.fc1_b))  # u := GELU'(pre-activation)
     x2 = ops.gemm_bias_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1)
     saved = (x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g) if save else None
     return x2, saved
@@ -73,16 +95,19 @@ def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_d
     """dx2: [B*N, d] fp32 (dx2_bf16: optional bf16 copy).  Returns (dx0, dx0_bf16, grads in LayerParams order)."""
     x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g = saved
     dv = dx2_bf16 if dx2_bf16 is not None else ops.cast_bf16(dx2)
-    d_fc2_w = ops.gemm_wgrad(dv, g)
-    d_fc2_b = ops.colsum_bf16(dv)
+    d_fc2_w = ops.gemm_wgrad(dv, g, out=_slot(P.fc2_w))
+    d_fc2_b = ops.colsum_bf16(dv, out=_slot(P.fc2_b))
+    _ready(P.fc2_w, P.fc2_b)
     du = ops.gemm_dgrad_dgelu(dv, bf16_of(P.fc2_w), u)
-    d_fc1_w = ops.gemm_wgrad(du, b)
-    d_fc1_b = ops.colsum_bf16(du)
+    d_fc1_w = ops.gemm_wgrad(du, b, out=_slot(P.fc1_w))
+    d_fc1_b = ops.colsum_bf16(du, out=_slot(P.fc1_b))
+    _ready(P.fc1_w, P.fc1_b)
     db = ops.gemm_dgrad(du, bf16_of(P.fc1_w))
     dx1, dx1_bf16, _, _ = ops.layernorm_bwd(db, x1, mean2, rstd2, dres=dx2, want_bf16=True)
     dqkv = ops.flash_attn_bwd(qkv, o, dx1_bf16.view(B, N, -1), lse, B, N, H, causal).view(B * N, -1)
-    d_qkv_w = ops.gemm_wgrad(dqkv, a)
-    d_qkv_b = ops.colsum_bf16(dqkv)
+    d_qkv_w = ops.gemm_wgrad(dqkv, a, out=_slot(P.qkv_w))
+    d_qkv_b = ops.colsum_bf16(dqkv, out=_slot(P.qkv_b))
+    _ready(P.qkv_w, P.qkv_b)
     dx0 = dx0_bf16 = None
     if need_dx:
         da = ops.gemm_dgrad(dqkv, bf16_of(P.qkv_w))

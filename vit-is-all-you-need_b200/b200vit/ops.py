@@ -18,12 +18,48 @@ F32 = torch.float32
 launch_count = 0  # number of C-ABI compute calls issued (bench.py reports it as gpu_launches evidence)
 
 
-def _call(name, t, *args):
+# kernels launched per C-ABI call (memsets not counted); everything else launches exactly one kernel
+_KERNELS_PER_CALL = {"b200vit_flash_attn_bwd": 2, "b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3}
+
+_prof = None  # list of (start_event, end_event, flops) while profile_gemms() is active
+
+
+def _call(name, t, *args, flops=None):
     global launch_count
     lib = _cabi.lib_for(t)  # raises for CPU tensors / missing library / non-sm_100 devices
-    launch_count += 1
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
     args = tuple(_cabi.stream_ptr() if a is _STREAM else a for a in args)
+    if _prof is not None and flops is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _cabi.check(getattr(lib, name)(*args))
+        e1.record()
+        _prof.append((e0, e1, flops, name))
+        return
     _cabi.check(getattr(lib, name)(*args))
+
+
+def profile_gemms(fn, steps=1):
+    """Runs fn() `steps` times with a CUDA-event pair around every tcgen05 GEMM launch (on the launching stream).
+    Returns (total GEMM milliseconds, total algorithmic FLOPs, number of launches)."""
+    global _prof
+    _prof = []
+    try:
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in _prof)
+        fl = float(sum(f for _, _, f, _ in _prof))
+        n = len(_prof)
+        detail = {}
+        for e0, e1, f, name in _prof:
+            d = detail.setdefault(name, [0.0, 0.0, 0])
+            d[0] += e0.elapsed_time(e1); d[1] += f; d[2] += 1
+        profile_gemms.last_detail = {k: {"ms": v[0], "tflops": v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 else 0.0, "launches": v[2]}
+                                     for k, v in detail.items()}
+    finally:
+        _prof = None
+    return ms, fl, n
 
 
 def _chk(t, dtype, name):
@@ -39,24 +75,25 @@ def gemm_bias(x, w, bias=None):
     M, K = x.shape
     N = w.shape[0]
     y = torch.empty(M, N, device=x.device, dtype=BF16)
-    _call("b200vit_gemm_bias", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(y), M, N, K, stream_ptr())
+    _call("b200vit_gemm_bias", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(y), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
     return y
 
 
-def gemm_bias_gelu(x, w, bias=None, save_u=True):
+def gemm_bias_gelu(x, w, bias=None):
+    """g = GELU(x w^T + bias) and gprime = GELU'(x w^T + bias), both bf16 (gprime is what backward needs)."""
     M, K = x.shape
     N = w.shape[0]
     g = torch.empty(M, N, device=x.device, dtype=BF16)
-    u = torch.empty(M, N, device=x.device, dtype=BF16) if save_u else None
-    _call("b200vit_gemm_bias_gelu", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(g), ptr(u), M, N, K, stream_ptr())
-    return g, u
+    gp = torch.empty(M, N, device=x.device, dtype=BF16)
+    _call("b200vit_gemm_bias_gelu", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(g), ptr(gp), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
+    return g, gp
 
 
 def gemm_bias_residual(x, w, bias, resid):
     M, K = x.shape
     N = w.shape[0]
     out = torch.empty(M, N, device=x.device, dtype=F32)
-    _call("b200vit_gemm_bias_residual", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(_chk(resid, F32, "resid")), ptr(out), M, N, K, stream_ptr())
+    _call("b200vit_gemm_bias_residual", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(_chk(resid, F32, "resid")), ptr(out), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
     return out
 
 
@@ -64,7 +101,7 @@ def gemm_bias_f32(x, w, bias=None):
     M, K = x.shape
     N = w.shape[0]
     out = torch.empty(M, N, device=x.device, dtype=F32)
-    _call("b200vit_gemm_bias_f32", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(out), M, N, K, stream_ptr())
+    _call("b200vit_gemm_bias_f32", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(out), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
     return out
 
 
@@ -72,15 +109,16 @@ def gemm_dgrad(dy, w):
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty(M, K, device=dy.device, dtype=BF16)
-    _call("b200vit_gemm_dgrad", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(w, BF16, "w")), ptr(dx), M, N, K, stream_ptr())
+    _call("b200vit_gemm_dgrad", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(w, BF16, "w")), ptr(dx), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
     return dx
 
 
-def gemm_dgrad_dgelu(dy, w, u):
+def gemm_dgrad_dgelu(dy, w, gprime):
+    u = gprime
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty(M, K, device=dy.device, dtype=BF16)
-    _call("b200vit_gemm_dgrad_dgelu", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(w, BF16, "w")), ptr(_chk(u, BF16, "u")), ptr(dx), M, N, K, stream_ptr())
+    _call("b200vit_gemm_dgrad_dgelu", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(w, BF16, "w")), ptr(_chk(u, BF16, "u")), ptr(dx), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
     return dx
 
 
@@ -90,7 +128,9 @@ def gemm_wgrad(dy, x, out=None, accumulate=False):
     if out is None:
         out = torch.empty(N, K, device=dy.device, dtype=F32)
         accumulate = False
-    _call("b200vit_gemm_wgrad", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(x, BF16, "x")), ptr(_chk(out, F32, "dw")), M, N, K, 1 if accumulate else 0, stream_ptr())
+    elif tuple(out.shape) != (N, K):
+        out = out.view(N, K)
+    _call("b200vit_gemm_wgrad", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(x, BF16, "x")), ptr(_chk(out, F32, "dw")), M, N, K, 1 if accumulate else 0, stream_ptr(), flops=2.0 * M * N * K)
     return out
 
 

@@ -28,8 +28,8 @@ static void plan_splits(GemmShape& s, bool allow_split) {
 
 template <bool A_MN, bool B_MN, int BN, int KIND>
 static int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-                  const EpiParams& ep, bool allow_split, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
+                  const EpiParams& ep, void* out2, bool allow_split, cudaStream_t st) {
+  using Cfg = GemmCfg<BN, KIND>;
   GemmShape s;
   s.M = M; s.N = N; s.K = K;
   s.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
@@ -49,28 +49,38 @@ static int launch(const void* A, long long lda, const void* B, long long ldb, in
   else      rc = make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, 64);
   if (rc != OK) return rc;
 
+  // output tensor maps for the TMA-store epilogue (32-row slabs of 128 bytes)
+  CUtensorMap to = ta, to2 = ta;
+  if (KIND != EPI_PATCH_F32) {
+    if (epi_out_is_f32(KIND)) rc = make_tmap_2d_f32(&to, ep.out, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo, 32, 32);
+    else                      rc = make_tmap_2d_bf16(&to, ep.out, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo, 32, 64);
+    if (rc != OK) return rc;
+    if (KIND == EPI_GELU_BF16) {
+      rc = make_tmap_2d_bf16(&to2, out2, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo, 32, 64);
+      if (rc != OK) return rc;
+    }
+  }
+
   auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, KIND>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  Epilogue<KIND> epi;
-  epi.p = ep;
   int grid = s.total_work < num_sms() ? s.total_work : num_sms();
   if (g_debug[3] > 0 && grid > g_debug[3]) grid = g_debug[3];
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, s, epi);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, to, to2, s, ep);
   B200_CUDA(cudaGetLastError());
   return OK;
 }
 
 template <bool A_MN, bool B_MN, int KIND>
 static int launch_bn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-                     const EpiParams& ep, bool allow_split, cudaStream_t st) {
+                     const EpiParams& ep, bool allow_split, cudaStream_t st, void* out2 = nullptr) {
   // 128x256 tiles when N fills them; 128x128 otherwise (less padding waste for narrow outputs).
   const bool wide = (g_debug[4] == 256) || (g_debug[4] != 128 && (N % 256 == 0 || N >= 1024));
-  if (wide) return launch<A_MN, B_MN, 256, KIND>(A, lda, B, ldb, M, N, K, ep, allow_split, st);
-  return launch<A_MN, B_MN, 128, KIND>(A, lda, B, ldb, M, N, K, ep, allow_split, st);
+  if (wide) return launch<A_MN, B_MN, 256, KIND>(A, lda, B, ldb, M, N, K, ep, out2, allow_split, st);
+  return launch<A_MN, B_MN, 128, KIND>(A, lda, B, ldb, M, N, K, ep, out2, allow_split, st);
 }
 
 static int check_common(const void* a, const void* b, const void* c, int M, int N, int K) {
@@ -82,7 +92,7 @@ static int check_common(const void* a, const void* b, const void* c, int M, int 
 
 static EpiParams make_ep(void* out, long long ldo) {
   EpiParams ep;
-  ep.out = out; ep.ldo = ldo; ep.out2 = nullptr; ep.ldo2 = 0; ep.bias = nullptr;
+  ep.out = out; ep.ldo = ldo; ep.bias = nullptr;
   ep.aux = nullptr; ep.ldaux = 0; ep.pos = nullptr; ep.P = 1; ep.T = 1; ep.extra = 0;
   return ep;
 }
@@ -111,13 +121,14 @@ int b200vit_gemm_bias(const void* x, const void* w, const float* bias, void* y, 
   return launch_bn<false, false, EPI_BF16>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
 }
 
-int b200vit_gemm_bias_gelu(const void* x, const void* w, const float* bias, void* g, void* u, int M,
+int b200vit_gemm_bias_gelu(const void* x, const void* w, const float* bias, void* g, void* gprime, int M,
                            int N, int K, void* stream) {
   int rc = check_common(x, w, g, M, N, K);
   if (rc) return rc;
+  B200_REQUIRE(gprime != nullptr, "gemm_bias_gelu: gprime is null");
   EpiParams ep = make_ep(g, N);
-  ep.bias = bias; ep.out2 = u; ep.ldo2 = N;
-  return launch_bn<false, false, EPI_GELU_BF16>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
+  ep.bias = bias;
+  return launch_bn<false, false, EPI_GELU_BF16>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream, gprime);
 }
 
 int b200vit_gemm_bias_residual(const void* x, const void* w, const float* bias, const float* resid,
@@ -148,14 +159,14 @@ int b200vit_gemm_dgrad(const void* dy, const void* w, void* dx, int M, int N, in
                                           (cudaStream_t)stream);
 }
 
-int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* u, void* dx, int M, int N,
+int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* gprime, void* dx, int M, int N,
                              int K, void* stream) {
   int rc = check_common(dy, w, dx, M, N, K);
   if (rc) return rc;
-  B200_REQUIRE(u != nullptr, "gemm_dgrad_dgelu: u is null");
+  B200_REQUIRE(gprime != nullptr, "gemm_dgrad_dgelu: gprime is null");
   EpiParams ep = make_ep(dx, K);
-  ep.aux = u; ep.ldaux = K;
-  return launch_bn<false, true, EPI_DGELU_BF16>(dy, N, w, K, M, K, N, ep, false, (cudaStream_t)stream);
+  ep.aux = gprime; ep.ldaux = K;
+  return launch_bn<false, true, EPI_MUL_BF16>(dy, N, w, K, M, K, N, ep, false, (cudaStream_t)stream);
 }
 
 // dw[N,K] = dy[M,N]^T x[M,K]: output rows = N, output cols = K, contraction over M (split-K).

@@ -1,5 +1,6 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
-// (fp32 accumulators in TMEM, double buffered) -> tcgen05.ld epilogue with fused element-wise work.
+// (fp32 accumulators in TMEM, double buffered) -> tcgen05.ld epilogue with fused element-wise work ->
+// swizzled smem staging -> TMA store (or TMA reduce-add for split-K).
 //
 //   D[M,N] = sum_k A(m,k) * B(n,k)
 //
@@ -12,8 +13,9 @@
 // with the canonical MN-major SWIZZLE_128B layout (LBO = distance between 64-wide MN groups,
 // SBO = distance between 8-row K groups).
 //
-// Warp roles (256 threads, 1 CTA/SM): warp0 = TMA producer, warp1 = MMA issuer (one thread),
-// warp2 = TMEM allocator, warps 4..7 = epilogue (each owns 32 TMEM lanes = 32 output rows).
+// Warp roles (384 threads, 1 CTA/SM): warp0 = TMA producer, warp1 = MMA issuer (one thread),
+// warp2 = TMEM allocator, warps 4..11 = epilogue.  Epilogue warp e owns TMEM lanes 32*(e%4).. (32 output rows)
+// and the column half e/4 of the tile, so two warps share each lane quarter.
 #pragma once
 #include "common.cuh"
 
@@ -21,7 +23,8 @@ namespace b200 {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARPS = 8;
 
 struct GemmShape {
   int M, N, K;
@@ -36,19 +39,21 @@ struct GemmShape {
 
 enum EpiKind : int {
   EPI_BF16 = 0,        // out(bf16) = acc + bias
-  EPI_GELU_BF16 = 1,   // out2(bf16) = u = acc + bias (optional) ; out(bf16) = gelu(u)
+  EPI_GELU_BF16 = 1,   // u = acc + bias ; out(bf16) = gelu(u) ; out2(bf16) = gelu'(u)   (both TMA-stored)
   EPI_RESID_F32 = 2,   // out(f32) = aux(f32) + acc + bias
-  EPI_DGELU_BF16 = 3,  // out(bf16) = acc * gelu'(aux(bf16))
+  EPI_MUL_BF16 = 3,    // out(bf16) = acc * aux(bf16)        (dgrad through GELU: aux = gelu'(u))
   EPI_F32 = 4,         // out(f32) = acc + bias
-  EPI_ATOMIC_F32 = 5,  // out(f32) += acc   (split-K wgrad)
-  EPI_PATCH_F32 = 6,   // out(f32)[b*T + extra + p] = acc + bias + pos[p]   (row = b*P + p)
+  EPI_ATOMIC_F32 = 5,  // out(f32) += acc   (split-K wgrad, TMA reduce-add)
+  EPI_PATCH_F32 = 6,   // out(f32)[b*T + extra + p] = acc + bias + pos[p]   (row = b*P + p), direct stores
 };
+
+__host__ __device__ constexpr bool epi_out_is_f32(int kind) {
+  return kind == EPI_RESID_F32 || kind == EPI_F32 || kind == EPI_ATOMIC_F32 || kind == EPI_PATCH_F32;
+}
 
 struct EpiParams {
   void* out;
   long long ldo;
-  void* out2;
-  long long ldo2;
   const float* bias;
   const void* aux;
   long long ldaux;
@@ -56,152 +61,74 @@ struct EpiParams {
   int P, T, extra;
 };
 
-template <int KIND>
-struct Epilogue {
-  EpiParams p;
+// GELU (exact erf form, nn.GELU() default) and its derivative from ONE exponential:
+//   erf(z) ~= 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z)   (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7)
+// with z = |u| / sqrt(2), so exp(-z^2) = exp(-u^2 / 2) is also the Gaussian of the derivative.
+__device__ __forceinline__ void gelu_and_grad(float u, float& g, float& gp) {
+  const float az = fabsf(u) * 0.70710678118654752f;
+  const float e = exp2f(-0.72134752044448170f * u * u);  // exp(-u^2/2)
+  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float cdf = 0.5f + 0.5f * copysignf(erf_abs, u);
+  g = u * cdf;
+  gp = fmaf(u * 0.39894228040143268f, e, cdf);
+}
 
-  // One thread owns output row `row`, columns [col, col+32); nvalid (multiple of 8) of them exist.
-  __device__ __forceinline__ void operator()(int row, int col, const uint32_t (&acc)[32],
-                                             int nvalid) const {
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-
-    if constexpr (KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_RESID_F32 ||
-                  KIND == EPI_F32 || KIND == EPI_PATCH_F32) {
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (q * 4 < nvalid) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col) + q);
-            v[q * 4 + 0] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
-          }
-        }
-      }
-    }
-
-    if constexpr (KIND == EPI_BF16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q * 8 < nvalid) {
-          uint4 w;
-          w.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); w.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-          w.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); w.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-          reinterpret_cast<uint4*>(o)[q] = w;
-        }
-      }
-    } else if constexpr (KIND == EPI_GELU_BF16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col;
-      __nv_bfloat16* o2 =
-          p.out2 ? reinterpret_cast<__nv_bfloat16*>(p.out2) + (long long)row * p.ldo2 + col : nullptr;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q * 8 < nvalid) {
-          uint4 w;
-          if (o2 != nullptr) {
-            w.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]); w.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-            w.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]); w.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-            reinterpret_cast<uint4*>(o2)[q] = w;
-          }
-          float g[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // GELU is applied to the bf16-rounded pre-activation, which is what backward sees.
-            const float u = __bfloat162float(__float2bfloat16_rn(v[q * 8 + j]));
-            g[j] = gelu_erf(u);
-          }
-          w.x = pack_bf16(g[0], g[1]); w.y = pack_bf16(g[2], g[3]);
-          w.z = pack_bf16(g[4], g[5]); w.w = pack_bf16(g[6], g[7]);
-          reinterpret_cast<uint4*>(o)[q] = w;
-        }
-      }
-    } else if constexpr (KIND == EPI_RESID_F32) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-      const float* r = reinterpret_cast<const float*>(p.aux) + (long long)row * p.ldaux + col;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q * 4 < nvalid) {
-          const float4 a = reinterpret_cast<const float4*>(r)[q];
-          float4 w;
-          w.x = a.x + v[q * 4 + 0]; w.y = a.y + v[q * 4 + 1];
-          w.z = a.z + v[q * 4 + 2]; w.w = a.w + v[q * 4 + 3];
-          reinterpret_cast<float4*>(o)[q] = w;
-        }
-      }
-    } else if constexpr (KIND == EPI_DGELU_BF16) {
-      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col;
-      const __nv_bfloat16* u =
-          reinterpret_cast<const __nv_bfloat16*>(p.aux) + (long long)row * p.ldaux + col;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q * 8 < nvalid) {
-          const uint4 uu = reinterpret_cast<const uint4*>(u)[q];
-          const float2 u0 = unpack_bf16(uu.x), u1 = unpack_bf16(uu.y), u2 = unpack_bf16(uu.z),
-                       u3 = unpack_bf16(uu.w);
-          uint4 w;
-          w.x = pack_bf16(v[q * 8 + 0] * gelu_erf_grad(u0.x), v[q * 8 + 1] * gelu_erf_grad(u0.y));
-          w.y = pack_bf16(v[q * 8 + 2] * gelu_erf_grad(u1.x), v[q * 8 + 3] * gelu_erf_grad(u1.y));
-          w.z = pack_bf16(v[q * 8 + 4] * gelu_erf_grad(u2.x), v[q * 8 + 5] * gelu_erf_grad(u2.y));
-          w.w = pack_bf16(v[q * 8 + 6] * gelu_erf_grad(u3.x), v[q * 8 + 7] * gelu_erf_grad(u3.y));
-          reinterpret_cast<uint4*>(o)[q] = w;
-        }
-      }
-    } else if constexpr (KIND == EPI_F32) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q * 4 < nvalid) {
-          reinterpret_cast<float4*>(o)[q] =
-              make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-        }
-      }
-    } else if constexpr (KIND == EPI_ATOMIC_F32) {
-      float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < nvalid) atomicAdd(o + j, v[j]);
-      }
-    } else if constexpr (KIND == EPI_PATCH_F32) {
-      const int b = row / p.P;
-      const int pp = row - b * p.P;
-      float* o = reinterpret_cast<float*>(p.out) + ((long long)b * p.T + p.extra + pp) * p.ldo + col;
-      const float* pe = p.pos + (long long)pp * p.ldaux + col;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q * 4 < nvalid) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(pe) + q);
-          reinterpret_cast<float4*>(o)[q] =
-              make_float4(v[q * 4 + 0] + a.x, v[q * 4 + 1] + a.y, v[q * 4 + 2] + a.z,
-                          v[q * 4 + 3] + a.w);
-        }
-      }
-    }
-  }
-};
-
-template <int BN>
+template <int BN, int KIND>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;       // 32 KB (BN=256) / 16 KB (BN=128)
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int SLABS = (KIND == EPI_GELU_BF16) ? 2 : 1;  // staging slabs (32 rows x 128 B) per epilogue warp
+  static constexpr int EPI_BYTES = GEMM_EPI_WARPS * SLABS * 4096;
+  static constexpr int STAGES = (200 * 1024 + 28 * 1024 - EPI_BYTES) / STAGE_BYTES > 6
+                                    ? 6 : (200 * 1024 + 28 * 1024 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages (512 or 256 columns)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
+
+// ---- TMA store helpers (smem tile -> global, bulk async group) ----
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 16-byte chunk j (0..7) of row r inside a 32-row x 128-byte slab with the TMA 128B swizzle
+__device__ __forceinline__ uint4* slab_chunk(uint8_t* slab, int r, int j) {
+  return reinterpret_cast<uint4*>(slab + r * 128 + ((j ^ (r & 7)) << 4));
+}
 
 template <bool A_MN, bool B_MN, int BN, int KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
-                    const __grid_constant__ CUtensorMap tma_b, const GemmShape s,
-                    const Epilogue<KIND> epi) {
-  using Cfg = GemmCfg<BN>;
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
+                    const GemmShape s, const EpiParams ep) {
+  using Cfg = GemmCfg<BN, KIND>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr bool OUT_F32 = epi_out_is_f32(KIND);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_epi = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -213,13 +140,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (KIND != EPI_PATCH_F32) tma_prefetch_desc(&tma_out);
+    if (KIND == EPI_GELU_BF16) tma_prefetch_desc(&tma_out2);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -305,31 +234,143 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
     }
   } else if (warp >= 4) {
     // ------------------------------- epilogue -----------------------------------
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int ew = warp - 4;
+    const int quarter = ew & 3;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int half = ew >> 2;    // column half of the tile
+    constexpr int NCH = BN / 2 / 32;  // 32-column chunks per warp
+    uint8_t* slab0 = smem_epi + ew * Cfg::SLABS * 4096;
+    uint8_t* slab1 = slab0 + 4096;  // GELU kind only
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < s.total_work; w += gridDim.x) {
       const int t = w / s.splits;
-      const int n0 = (t % s.tiles_n) * BN;
-      const int m0 = (t / s.tiles_n) * GEMM_BM;
+      const int n0 = (t % s.tiles_n) * BN + half * (BN / 2);
+      const int m0 = (t / s.tiles_n) * GEMM_BM + quarter * 32;
       mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
       tc_fence_after();
-      const int row = m0 + ew * 32 + lane;
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        const int nvalid = min(32, s.N - (n0 + c));
-        if (nvalid <= 0) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
+      const int row = m0 + lane;
+      const bool row_ok = row < s.M;
+      const uint32_t taddr = tmem_base + acc * BN + half * (BN / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
+      uint32_t vbuf[2][32];
+      tmem_ld32(taddr, vbuf[0]);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         tmem_ld_wait();
-        if (row < s.M) epi(row, n0 + c, v, nvalid);
+        if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
+        const int col = n0 + c * 32;
+        if (col < s.N) {  // warp-uniform
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vbuf[c & 1][j]);
+          if constexpr (KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_RESID_F32 || KIND == EPI_F32 ||
+                        KIND == EPI_PATCH_F32) {
+            if (ep.bias != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (col + q * 4 < s.N) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col) + q);
+                  v[q * 4 + 0] += b.x; v[q * 4 + 1] += b.y; v[q * 4 + 2] += b.z; v[q * 4 + 3] += b.w;
+                }
+              }
+            }
+          }
+          if constexpr (KIND == EPI_PATCH_F32) {
+            // direct stores: output rows are remapped per batch element, a TMA box cannot describe them
+            if (row_ok) {
+              const int b = row / ep.P, pp = row - b * ep.P;
+              float* o = reinterpret_cast<float*>(ep.out) + ((long long)b * ep.T + ep.extra + pp) * ep.ldo + col;
+              const float* pe = ep.pos + (long long)pp * ep.ldaux + col;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (col + q * 4 < s.N) {
+                  const float4 a = __ldg(reinterpret_cast<const float4*>(pe) + q);
+                  reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4 + 0] + a.x, v[q * 4 + 1] + a.y,
+                                                                v[q * 4 + 2] + a.z, v[q * 4 + 3] + a.w);
+                }
+              }
+            }
+          } else if constexpr (OUT_F32) {
+            // ---- fp32 output: one slab (32 rows x 32 cols) per chunk ----
+            if constexpr (KIND == EPI_RESID_F32) {
+              if (row_ok) {
+                const float* r = reinterpret_cast<const float*>(ep.aux) + (long long)row * ep.ldaux + col;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  if (col + q * 4 < s.N) {
+                    const float4 a = reinterpret_cast<const float4*>(r)[q];
+                    v[q * 4 + 0] += a.x; v[q * 4 + 1] += a.y; v[q * 4 + 2] += a.z; v[q * 4 + 3] += a.w;
+                  }
+                }
+              }
+            }
+            if (lane == 0) tma_store_wait_read();  // the previous store has finished reading the slab
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *slab_chunk(slab0, lane, q) = make_uint4(__float_as_uint(v[q * 4 + 0]), __float_as_uint(v[q * 4 + 1]),
+                                                       __float_as_uint(v[q * 4 + 2]), __float_as_uint(v[q * 4 + 3]));
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (KIND == EPI_ATOMIC_F32) tma_reduce_add_2d(&tma_out, slab0, col, m0);
+              else                                  tma_store_2d(&tma_out, slab0, col, m0);
+              tma_store_commit();
+            }
+          } else {
+            // ---- bf16 output: a slab holds 64 columns = two chunks; store after the odd chunk ----
+            if constexpr (KIND == EPI_MUL_BF16) {
+              if (row_ok) {
+                const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)row * ep.ldaux + col;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (col + q * 8 < s.N) {
+                    const uint4 uu = reinterpret_cast<const uint4*>(a)[q];
+                    const float2 a0 = unpack_bf16(uu.x), a1 = unpack_bf16(uu.y), a2 = unpack_bf16(uu.z), a3 = unpack_bf16(uu.w);
+                    v[q * 8 + 0] *= a0.x; v[q * 8 + 1] *= a0.y; v[q * 8 + 2] *= a1.x; v[q * 8 + 3] *= a1.y;
+                    v[q * 8 + 4] *= a2.x; v[q * 8 + 5] *= a2.y; v[q * 8 + 6] *= a3.x; v[q * 8 + 7] *= a3.y;
+                  }
+                }
+              }
+            }
+            float gp[32];
+            if constexpr (KIND == EPI_GELU_BF16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) gelu_and_grad(v[j], v[j], gp[j]);
+            }
+            if ((c & 1) == 0) {
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              *slab_chunk(slab0, lane, (c & 1) * 4 + q) =
+                  make_uint4(pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                             pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+              if constexpr (KIND == EPI_GELU_BF16) {
+                *slab_chunk(slab1, lane, (c & 1) * 4 + q) =
+                    make_uint4(pack_bf16(gp[q * 8 + 0], gp[q * 8 + 1]), pack_bf16(gp[q * 8 + 2], gp[q * 8 + 3]),
+                               pack_bf16(gp[q * 8 + 4], gp[q * 8 + 5]), pack_bf16(gp[q * 8 + 6], gp[q * 8 + 7]));
+              }
+            }
+            if ((c & 1) == 1 || c == NCH - 1 || col + 32 >= s.N) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                const int c0 = n0 + (c & ~1) * 32;
+                tma_store_2d(&tma_out, slab0, c0, m0);
+                if constexpr (KIND == EPI_GELU_BF16) tma_store_2d(&tma_out2, slab1, c0, m0);
+                tma_store_commit();
+              }
+            }
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();

@@ -55,8 +55,8 @@ static int load_encode() {
   return OK;
 }
 
-int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, bool f32) {
   int rc = load_encode();
   if (rc != OK) return rc;
   cuuint64_t gdim[5];
@@ -80,7 +80,7 @@ int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64
       return ERR_ARG;
     }
   }
-  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+  CUresult r = g_encode(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
                         const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -93,12 +93,25 @@ int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64
   return OK;
 }
 
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  return make_tmap_nd(out, base, rank, dims, strides_bytes, box, swizzle128, false);
+}
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols) {
   const uint64_t dims[2] = {cols, rows};
   const uint64_t strides[2] = {2, ld * 2};
   const uint32_t box[2] = {box_cols, box_rows};
-  return make_tmap_nd_bf16(out, base, 2, dims, strides, box, true);
+  return make_tmap_nd(out, base, 2, dims, strides, box, true, false);
+}
+
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows, uint32_t box_cols) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[2] = {4, ld * 4};
+  const uint32_t box[2] = {box_cols, box_rows};
+  return make_tmap_nd(out, base, 2, dims, strides, box, true, true);
 }
 
 }  // namespace b200
