@@ -43,6 +43,12 @@ struct AttnParams {
   __nv_bfloat16* dqkv;         // [B, N, 3d]
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // K-major SWIZZLE_128B tile (rows of 128 bytes): descriptor for the 16-element K slice `k16` (0..3)
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k16) {
   return umma_smem_desc(tile_addr + k16 * 32, 16, 1024);
@@ -72,14 +78,15 @@ struct FwdSmem {
   static constexpr int KV = AT_TILE_BYTES;                  // 2 stages x (K | V)
   static constexpr int P = KV + 4 * AT_TILE_BYTES;          // 128 x 128 bf16 = 32 KB
   static constexpr int BAR = P + 2 * AT_TILE_BYTES;
-  static constexpr int TOTAL = BAR + 128 + 1024;            // + alignment slack
+  static constexpr int TOTAL = BAR + 128;                   // 114,816 B -> two CTAs per SM
 };
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
-  extern __shared__ uint8_t at_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t at_smem_raw[];
+  uint8_t* smem = at_smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte aligned bases
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
@@ -95,8 +102,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
   int nkv = (p.N + AT_BK - 1) / AT_BK;
   if (CAUSAL) nkv = min(nkv, (q0 + AT_BQ + AT_BK - 1) / AT_BK);
 
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm_qkv);
+  if (warp == 4 && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
     mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
@@ -104,6 +110,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
     mbar_init(p_ready, 128);
     mbar_init(o_full, 1);
     fence_barrier_init();
+    // first loads are issued before the CTA-wide sync so their latency overlaps the TMEM allocation
+    mbar_expect_tx(q_full, AT_TILE_BYTES);
+    tma_load_3d(smem + FwdSmem::Q, &tm_qkv, q_full, hh * AT_HD, q0, b);
+    for (int j = 0; j < min(nkv, 2); ++j) {
+      uint8_t* kdst = smem + FwdSmem::KV + j * 2 * AT_TILE_BYTES;
+      mbar_expect_tx(&kv_full[j], 2 * AT_TILE_BYTES);
+      tma_load_3d(kdst, &tm_qkv, &kv_full[j], p.d + hh * AT_HD, j * AT_BK, b);
+      tma_load_3d(kdst + AT_TILE_BYTES, &tm_qkv, &kv_full[j], 2 * p.d + hh * AT_HD, j * AT_BK, b);
+    }
   }
   if (warp == 5) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
   tc_fence_before();
@@ -115,9 +130,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
 
   if (warp == 4) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, AT_TILE_BYTES);
-      tma_load_3d(smem + FwdSmem::Q, &tm_qkv, q_full, hh * AT_HD, q0, b);
-      for (int j = 0; j < nkv; ++j) {
+      for (int j = 2; j < nkv; ++j) {
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1, 10);
         uint8_t* kdst = smem + FwdSmem::KV + st * 2 * AT_TILE_BYTES;
@@ -128,7 +141,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, AT_BK, false, false);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, AT_HD, false, true);
       const uint32_t sQ = smem_u32(smem + FwdSmem::Q);
       const uint32_t sP = smem_u32(smem + FwdSmem::P);
@@ -137,6 +149,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         const int st = j & 1;
         const uint32_t sK = smem_u32(smem + FwdSmem::KV + st * 2 * AT_TILE_BYTES);
         const uint32_t sV = sK + AT_TILE_BYTES;
+        const int nkeys = min(AT_BK, p.N - j * AT_BK);     // valid keys of this block
+        const int ncols = ((nkeys + 31) >> 5) << 5;        // S columns the softmax warps will read
+        const uint32_t idesc_s = umma_idesc_bf16(128, ncols, false, false);
         mbar_wait(&kv_full[st], (j >> 1) & 1, 21);
         tc_fence_after();
 #pragma unroll
@@ -144,8 +159,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         umma_commit(s_full);
         mbar_wait(p_ready, j & 1, 22);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
+        const int ksteps = (nkeys + 15) >> 4;              // P columns beyond the valid keys are zero / unused
+        for (int k = 0; k < ksteps; ++k)
           umma_bf16(tmem_O, desc_kmajor(sP + (k >> 2) * AT_TILE_BYTES, k & 3), desc_mnmajor(sV, k, 8192), idesc_o, k > 0);
         umma_commit(o_full);
         umma_commit(&kv_empty[st]);
@@ -156,12 +171,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
     const int r = threadIdx.x;  // 0..127 == TMEM lane
     const int q = q0 + r;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const bool warp_has_rows = q0 + warp * 32 < p.N;  // warp-uniform: rows beyond the sequence do no math
     float m = -INFINITY, l = 0.f;
     float oacc[AT_HD];
 #pragma unroll
     for (int i = 0; i < AT_HD; ++i) oacc[i] = 0.f;
 
     for (int j = 0; j < nkv; ++j) {
+      if (!warp_has_rows) {  // stay in phase with the pipeline, contribute nothing
+        mbar_wait(s_full, j & 1, 33);
+        mbar_arrive(p_ready);
+        continue;
+      }
+      const int nch = (min(AT_BK, p.N - j * AT_BK) + 31) >> 5;  // 32-key chunks holding at least one valid key
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1, 30);
         tc_fence_after();
@@ -180,7 +202,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
       // pass 1: row maximum
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < nch; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_off + c * 32, v);
         tmem_ld_wait();
@@ -198,22 +220,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
       }
       float m_new = fmaxf(m, mx * p.scale_log2e);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m - m_use);
+      const float alpha = ex2_approx(m - m_use);
       l *= alpha;
 #pragma unroll
       for (int i = 0; i < AT_HD; ++i) oacc[i] *= alpha;
       // pass 2: probabilities -> bf16 operand tile
       float rowsum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < nch; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_off + c * 32, v);
         tmem_ld_wait();
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2e, -m_use));
-          float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, -m_use));
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, -m_use));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, -m_use));
           if (need_mask) {
             const int key = j * AT_BK + c * 32 + i;
             if (!(key < p.N && (!CAUSAL || key <= q))) p0 = 0.f;
@@ -231,6 +253,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
       mbar_arrive(p_ready);
     }
     // last PV
+    if (warp_has_rows) {
     mbar_wait(o_full, (nkv - 1) & 1, 32);
     tc_fence_after();
     {
@@ -256,6 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         reinterpret_cast<uint4*>(orow)[c] = w;
       }
       if (p.lse != nullptr) p.lse[((long long)b * p.H + hh) * p.N + q] = m * LN2 + logf(l);
+    }
     }
   }
 
@@ -409,7 +433,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           for (int e = 0; e < 2; ++e) {
             const int key = k0 + c * 32 + i + e;
             const bool ok = qv && key < p.N && (!CAUSAL || key <= q);
-            const float pe = ok ? exp2f(fmaf(__uint_as_float(s[i + e]), p.scale_log2e, -lse2)) : 0.f;
+            const float pe = ok ? ex2_approx(fmaf(__uint_as_float(s[i + e]), p.scale_log2e, -lse2)) : 0.f;
             pv[e] = pe;
             dv[e] = pe * (__uint_as_float(dp[i + e]) - Dq) * p.scale;
           }
