@@ -1,0 +1,100 @@
+"""Drop-in boundary checks that run on CPU: constructors, public attributes and state_dict keys/shapes of the
+drop-in modules equal the reference's (compared live when /root/reference is present, and always against the key
+lists frozen in the golden fixtures)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "vit-is-all-you-need_b200")
+REF = "/root/reference"
+
+
+def test_transformer_surface_matches_fixture_keys(golden_dir):
+    from b200vit import modules as M
+    g = np.load(os.path.join(golden_dir, "transformer.npz"))
+    cfg = M.TransformerConfig(n_layers=2, n_heads=1, n_embd=64, block_size=16, causal=True, dropout=0.0)
+    assert cfg.head_dim == 64
+    m = M.Transformer(cfg)
+    for attr in ("n_layers", "n_heads", "n_embd", "block_size", "causal", "dropout", "head_dim"):
+        assert hasattr(m, attr) and hasattr(m.layers[0], attr) and hasattr(m.layers[0].multi_attn, attr)
+    ref_keys = sorted(k[len("b_w_"):] for k in g.files if k.startswith("b_w_"))
+    ours = sorted(k for k in m.state_dict() if not k.endswith("mask"))
+    assert ours == ref_keys
+    for k in ours:
+        assert tuple(m.state_dict()[k].shape) == g["b_w_" + k].shape
+    assert m.state_dict()["layers.0.multi_attn.mask"].shape == (16, 16)
+    assert set(M.transformer_configs) >= {"S", "B", "L"}
+    assert (M.B(block_size=197).n_embd, M.L(block_size=197).n_layers, M.S(block_size=1).n_heads) == (768, 24, 8)
+
+
+def test_resblock_and_vq_surface(golden_dir):
+    from b200vit import modules as M
+    g = np.load(os.path.join(golden_dir, "resblock.npz"))
+    blk = M.ResidualAttentionBlock(128, 2)
+    assert sorted(blk.state_dict()) == sorted(k[2:] for k in g.files if k.startswith("w_"))
+    assert "mlp.c_fc.weight" in blk.state_dict() and "attn.in_proj_weight" in blk.state_dict()
+    blk0 = M.ResidualAttentionBlock(128, 2, mlp_ratio=0)
+    assert not any(k.startswith("mlp") or k.startswith("ln_2") for k in blk0.state_dict())
+    vq = M.VectorQuantizer(codebook_size=32, token_size=12, use_l2_norm=True)
+    assert list(vq.state_dict()) == ["embedding.weight"] and vq.embedding.weight.abs().max() <= 1 / 32
+    with pytest.raises(NotImplementedError):
+        M.VectorQuantizer(clustering_vq=True)
+    e = vq.get_codebook_entry(torch.tensor([0, 5]))
+    torch.testing.assert_close(e.norm(dim=-1), torch.ones(2))
+
+
+def test_unsupported_configs_fail_loudly():
+    from b200vit import modules as M
+    with pytest.raises(NotImplementedError):
+        M.Transformer(M.TransformerConfig(n_layers=1, n_heads=4, n_embd=128, block_size=8))  # head_dim 32
+    with pytest.raises(NotImplementedError):
+        M.Transformer(M.TransformerConfig(n_layers=1, n_heads=2, n_embd=128, block_size=8, dropout=0.1))
+    m = M.Transformer(M.TransformerConfig(n_layers=1, n_heads=2, n_embd=128, block_size=8))
+    with pytest.raises(Exception):
+        m(torch.zeros(1, 8, 128))  # CPU tensors: no fallback
+
+
+_LIVE = r"""
+import json, os, sys, types
+mode, ref, pkg = sys.argv[1], sys.argv[2], sys.argv[3]
+os.environ["WANDB_MODE"] = "disabled"
+if mode == "dropin":
+    sys.path.insert(0, pkg)
+    from b200vit import launch
+    launch.install_import_shims(ref)
+    launch.install_class_swap(main_only=False)
+else:
+    sys.path.insert(0, ref)
+    sys.modules["lpips"] = types.ModuleType("lpips")
+    m = types.ModuleType("vector_quantize_pytorch"); m.FSQ = object; sys.modules["vector_quantize_pytorch"] = m
+import torch
+import transformer, train_vit, train_titok
+out = {}
+transformer.transformer_configs.setdefault("Ti", lambda **kw: transformer.TransformerConfig(12, 3, 192, **kw))
+vit = train_vit.ViTClassifier(train_vit.ViTConfig(32, 3, 4, "Ti", 1, 0.0), num_classes=10)
+out["vit"] = {k: list(v.shape) for k, v in vit.state_dict().items()}
+titok = train_titok.TiTok(train_titok.TiTokConfig(256, 16, 32, 4096, 12, "S"))
+out["titok"] = {k: list(v.shape) for k, v in titok.state_dict().items()}
+out["classes"] = [type(titok.enc.vit).__module__, type(titok.quant).__module__, type(vit.vit.transformer).__module__]
+print("RESULT" + json.dumps(out))
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_launcher_swaps_classes_and_keeps_state_dict_contract():
+    def run(mode):
+        r = subprocess.run([sys.executable, "-c", _LIVE, mode, REF, PKG], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")][-1]
+        return json.loads(line[len("RESULT"):])
+    ref, ours = run("reference"), run("dropin")
+    assert ours["vit"] == ref["vit"], "ViTClassifier state_dict keys/shapes must equal the reference's"
+    assert ours["titok"] == ref["titok"], "TiTok (train_titok.py) state_dict keys/shapes must equal the reference's"
+    assert all(c.startswith("b200vit") for c in ours["classes"]), ours["classes"]
+    assert not any(c.startswith("b200vit") for c in ref["classes"])

@@ -1,0 +1,106 @@
+"""Runs one of the reference's training scripts UNCHANGED on top of the drop-in modules:
+
+    python -m b200vit.launch /path/to/reference/train_vit.py --transformer B --dropout 0.0 --epochs 1 ...
+    B200VIT_SYNTHETIC=1 python -m b200vit.launch /path/to/reference/train_titok.py ...
+
+What it does:
+  * puts ../shim ahead of the reference directory on sys.path, so `from transformer import ...`,
+    `from train_vit import ViTConfig, ViT` and `import blocks` resolve to the sm_100a-backed classes;
+  * classes the executed script defines itself (`ViT` in train_vit.py:30, `Quantizer` in train_titok.py:45 /
+    train_vit_vqgan.py:45) are swapped at class-creation time through builtins.__build_class__;
+  * stubs two imports the scripts never use (lpips, vector_quantize_pytorch.FSQ) when they are not installed,
+    disables wandb, and (B200VIT_SYNTHETIC=1) replaces the hard-coded ImageNet loaders with synthetic ones.
+"""
+import builtins
+import os
+import runpy
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SHIM = os.path.join(os.path.dirname(HERE), "shim")
+
+_SWAP = {"ViT": "ViT", "Quantizer": "Quantizer"}  # name defined by the script -> name in b200vit.modules
+
+
+def install_import_shims(reference_dir):
+    for p in (reference_dir, SHIM, os.path.dirname(HERE)):
+        if p in sys.path:
+            sys.path.remove(p)
+    sys.path.insert(0, reference_dir)
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, SHIM)  # shim first: bare `transformer`, `train_vit`, `blocks` resolve here
+    os.environ.setdefault("WANDB_MODE", "disabled")
+    try:
+        import lpips  # noqa: F401
+    except Exception:
+        sys.modules["lpips"] = types.ModuleType("lpips")
+    try:
+        import vector_quantize_pytorch  # noqa: F401
+    except Exception:
+        m = types.ModuleType("vector_quantize_pytorch")
+        m.FSQ = object
+        sys.modules["vector_quantize_pytorch"] = m
+
+
+def install_class_swap(main_only=True):
+    """Classes named in _SWAP that the script defines as nn.Module subclasses are replaced by the drop-ins."""
+    import torch.nn as nn
+
+    from . import modules
+    orig = builtins.__build_class__
+
+    def build_class(func, name, *bases, **kw):
+        if name in _SWAP and any(isinstance(b, type) and issubclass(b, nn.Module) for b in bases):
+            mod = func.__globals__.get("__name__", "")
+            if not main_only or mod == "__main__":
+                return getattr(modules, _SWAP[name])
+        return orig(func, name, *bases, **kw)
+
+    builtins.__build_class__ = build_class
+    return orig
+
+
+def install_synthetic_loaders():
+    """datasets.get_imagenet_loaders has a hard-coded dataset root (datasets.py:7,23); benchmarks and smoke runs
+    use synthetic tensors of the same shapes instead."""
+    import datasets
+    import torch
+
+    class _Synthetic(torch.utils.data.Dataset):
+        def __init__(self, n, size):
+            self.n, self.size = n, size
+
+        def __len__(self):
+            return self.n
+
+        def __getitem__(self, i):
+            g = torch.Generator().manual_seed(i)
+            return torch.rand(3, self.size, self.size, generator=g), int(torch.randint(0, 1000, (1,), generator=g))
+
+    def get_imagenet_loaders(image_size, bs, *a, **k):
+        n = int(os.environ.get("B200VIT_SYNTHETIC_SAMPLES", 64 * bs))
+        mk = lambda m: torch.utils.data.DataLoader(_Synthetic(m, image_size), batch_size=bs, shuffle=False, num_workers=0)  # noqa: E731
+        return mk(n), mk(max(bs, n // 8))
+
+    datasets.get_imagenet_loaders = get_imagenet_loaders
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        raise SystemExit(__doc__)
+    script = os.path.abspath(argv[0])
+    install_import_shims(os.path.dirname(script))
+    if os.environ.get("B200VIT_SYNTHETIC", "0") == "1":
+        install_synthetic_loaders()
+    orig = install_class_swap()
+    sys.argv = [script] + argv[1:]
+    try:
+        runpy.run_path(script, run_name="__main__")
+    finally:
+        builtins.__build_class__ = orig
+
+
+if __name__ == "__main__":
+    main()
