@@ -497,6 +497,228 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// --------------------------------------------------------------------------------------------------
+// Backward for short sequences (N <= 256: ViT-Ti/B/L token counts 65 / 197): one CTA per (batch, head) keeps
+// K, V, Q and dO of the whole head resident in shared memory and ALL gradient accumulators in TMEM
+// (dV_j, dK_j per key block, dQ_0 and dQ_1 across key blocks), so nothing is accumulated through HBM:
+// no fp32 dQ buffer, no atomics, no conversion pass, and every operand tile is loaded exactly once.
+// --------------------------------------------------------------------------------------------------
+struct BwdSmallSmem {
+  static constexpr int K = 0;                               // 2 tiles
+  static constexpr int V = 2 * AT_TILE_BYTES;               // 2 tiles
+  static constexpr int Q = 4 * AT_TILE_BYTES;               // 2 tiles
+  static constexpr int DO = 6 * AT_TILE_BYTES;              // 2 tiles
+  static constexpr int P = 8 * AT_TILE_BYTES;               // 32 KB
+  static constexpr int DS = P + 2 * AT_TILE_BYTES;          // 32 KB
+  static constexpr int BAR = DS + 2 * AT_TILE_BYTES;
+  static constexpr int TOTAL = BAR + 128;
+};
+
+template <bool CAUSAL>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                      const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t at_smem_raw[];
+  uint8_t* smem = at_smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmallSmem::BAR);
+  uint64_t* kv_full = bars + 0;    // [2]
+  uint64_t* q_full = bars + 2;     // [2]
+  uint64_t* sdp_full = bars + 4;
+  uint64_t* pds_ready = bars + 5;
+  uint64_t* mma_done = bars + 6;
+  uint64_t* dkv_free = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hh = blockIdx.x, b = blockIdx.y;
+  const int nt = (p.N + 127) / 128;  // 1 or 2 tiles along both queries and keys
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
+    mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_ready, 128);
+    mbar_init(mma_done, 1);
+    mbar_init(dkv_free, 128);
+    fence_barrier_init();
+    for (int t = 0; t < nt; ++t) {  // order: what the first iteration needs comes first
+      mbar_expect_tx(&kv_full[t], 2 * AT_TILE_BYTES);
+      tma_load_3d(smem + BwdSmallSmem::K + t * AT_TILE_BYTES, &tm_qkv, &kv_full[t], p.d + hh * AT_HD, t * 128, b);
+      tma_load_3d(smem + BwdSmallSmem::V + t * AT_TILE_BYTES, &tm_qkv, &kv_full[t], 2 * p.d + hh * AT_HD, t * 128, b);
+      mbar_expect_tx(&q_full[t], 2 * AT_TILE_BYTES);
+      tma_load_3d(smem + BwdSmallSmem::Q + t * AT_TILE_BYTES, &tm_qkv, &q_full[t], hh * AT_HD, t * 128, b);
+      tma_load_3d(smem + BwdSmallSmem::DO + t * AT_TILE_BYTES, &tm_do, &q_full[t], hh * AT_HD, t * 128, b);
+    }
+  }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256,
+                 tmem_dK = tmem_base + 320, tmem_dQ = tmem_base + 384;  // dQ_i at tmem_dQ + 64 * i
+
+  if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_t = umma_idesc_bf16(128, AT_HD, true, true);     // dV, dK
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, AT_HD, false, true);    // dQ
+      const uint32_t sP = smem_u32(smem + BwdSmallSmem::P), sDS = smem_u32(smem + BwdSmallSmem::DS);
+      int t = 0;
+      for (int j = 0; j < nt; ++j) {
+        const uint32_t sK = smem_u32(smem + BwdSmallSmem::K + j * AT_TILE_BYTES);
+        const uint32_t sV = smem_u32(smem + BwdSmallSmem::V + j * AT_TILE_BYTES);
+        const int nkeys = min(128, p.N - j * 128);
+        const int ncols = ((nkeys + 31) >> 5) << 5;
+        const uint32_t idesc_s = umma_idesc_bf16(128, ncols, false, false);
+        const int kkeys = (nkeys + 15) >> 4;
+        mbar_wait(&kv_full[j], 0, 70);
+        if (j > 0) { mbar_wait(dkv_free, (j - 1) & 1, 71); }
+        const int first_i = CAUSAL ? j : 0;
+        for (int i = first_i; i < nt; ++i, ++t) {
+          const uint32_t sQ = smem_u32(smem + BwdSmallSmem::Q + i * AT_TILE_BYTES);
+          const uint32_t sDO = smem_u32(smem + BwdSmallSmem::DO + i * AT_TILE_BYTES);
+          const int krows = (min(128, p.N - i * 128) + 15) >> 4;
+          mbar_wait(&q_full[i], 0, 72);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_dP, desc_kmajor(sDO, k), desc_kmajor(sV, k), idesc_s, k > 0);
+          umma_commit(sdp_full);
+          mbar_wait(pds_ready, t & 1, 73);
+          tc_fence_after();
+          for (int k = 0; k < krows; ++k)
+            umma_bf16(tmem_dV, desc_mnmajor(sP, k, 16384), desc_mnmajor(sDO, k, 8192), idesc_t, (i > first_i || k > 0) ? 1u : 0u);
+          for (int k = 0; k < krows; ++k)
+            umma_bf16(tmem_dK, desc_mnmajor(sDS, k, 16384), desc_mnmajor(sQ, k, 8192), idesc_t, (i > first_i || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kkeys; ++k)
+            umma_bf16(tmem_dQ + 64 * i, desc_kmajor(sDS + (k >> 2) * AT_TILE_BYTES, k & 3), desc_mnmajor(sK, k, 8192), idesc_q,
+                      (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(mma_done);
+        }
+      }
+    }
+  } else if (warp < 4) {
+    const int r = threadIdx.x;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    float lse2[2] = {0.f, 0.f}, Dq[2] = {0.f, 0.f};
+    int t = 0;
+    for (int j = 0; j < nt; ++j) {
+      const int k0 = j * 128;
+      const int nch = (min(128, p.N - k0) + 31) >> 5;
+      const int first_i = CAUSAL ? j : 0;
+      for (int i = first_i; i < nt; ++i, ++t) {
+        const int q = i * 128 + r;
+        const bool qv = q < p.N;
+        const bool warp_has_rows = i * 128 + warp * 32 < p.N;
+        if (j == 0 && qv) {  // first visit of query tile i: row statistics
+          lse2[i] = p.lse[((long long)b * p.H + hh) * p.N + q] * LOG2E;
+          const uint4* orow = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD);
+          const uint4* drow = reinterpret_cast<const uint4*>(p.do_in + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD);
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 a = orow[c], g = drow[c];
+            const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+            const float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
+            acc += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+          }
+          Dq[i] = acc;
+        }
+        const float my_lse = lse2[i], my_D = Dq[i];
+        mbar_wait(sdp_full, t & 1, 80);
+        if (t > 0) mbar_wait(mma_done, (t - 1) & 1, 81);  // previous dV/dK/dQ MMAs no longer read P / dS
+        tc_fence_after();
+        if (warp_has_rows) {
+#pragma unroll 1
+          for (int c = 0; c < nch; ++c) {
+            uint32_t s[32], dp[32];
+            tmem_ld32(tmem_S + lane_off + c * 32, s);
+            tmem_ld32(tmem_dP + lane_off + c * 32, dp);
+            tmem_ld_wait();
+            uint32_t wp[16], wd[16];
+#pragma unroll
+            for (int e2 = 0; e2 < 32; e2 += 2) {
+              float pv[2], dv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int key = k0 + c * 32 + e2 + e;
+                const bool ok = qv && key < p.N && (!CAUSAL || key <= q);
+                const float pe = ok ? ex2_approx(fmaf(__uint_as_float(s[e2 + e]), p.scale_log2e, -my_lse)) : 0.f;
+                pv[e] = pe;
+                dv[e] = pe * (__uint_as_float(dp[e2 + e]) - my_D) * p.scale;
+              }
+              wp[e2 >> 1] = pack_bf16(pv[0], pv[1]);
+              wd[e2 >> 1] = pack_bf16(dv[0], dv[1]);
+            }
+            store_operand_chunk(smem + BwdSmallSmem::P, r, c, wp);
+            store_operand_chunk(smem + BwdSmallSmem::DS, r, c, wd);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(pds_ready);
+      }
+      // dK_j / dV_j are complete once the last MMA batch of this key block has finished
+      mbar_wait(mma_done, (t - 1) & 1, 82);
+      tc_fence_after();
+      const int key = k0 + r;
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {  // 0: dK, 1: dV
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_off + c * 32, v);
+          tmem_ld_wait();
+          if (key < p.N) {
+            __nv_bfloat16* dst = p.dqkv + ((long long)b * p.sb + key * p.sn) * 3 * p.d + (which + 1) * p.d + hh * AT_HD + c * 32;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              uint4 w;
+              w.x = pack_bf16(__uint_as_float(v[i4 * 8 + 0]), __uint_as_float(v[i4 * 8 + 1]));
+              w.y = pack_bf16(__uint_as_float(v[i4 * 8 + 2]), __uint_as_float(v[i4 * 8 + 3]));
+              w.z = pack_bf16(__uint_as_float(v[i4 * 8 + 4]), __uint_as_float(v[i4 * 8 + 5]));
+              w.w = pack_bf16(__uint_as_float(v[i4 * 8 + 6]), __uint_as_float(v[i4 * 8 + 7]));
+              reinterpret_cast<uint4*>(dst)[i4] = w;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dkv_free);
+    }
+    // dQ of both query tiles (all MMAs have completed: the last mma_done was waited on above)
+    for (int i = 0; i < nt; ++i) {
+      const int q = i * 128 + r;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_dQ + 64 * i + lane_off + c * 32, v);
+        tmem_ld_wait();
+        if (q < p.N) {
+          __nv_bfloat16* dst = p.dqkv + ((long long)b * p.sb + q * p.sn) * 3 * p.d + hh * AT_HD + c * 32;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(v[i4 * 8 + 0]), __uint_as_float(v[i4 * 8 + 1]));
+            w.y = pack_bf16(__uint_as_float(v[i4 * 8 + 2]), __uint_as_float(v[i4 * 8 + 3]));
+            w.z = pack_bf16(__uint_as_float(v[i4 * 8 + 4]), __uint_as_float(v[i4 * 8 + 5]));
+            w.w = pack_bf16(__uint_as_float(v[i4 * 8 + 6]), __uint_as_float(v[i4 * 8 + 7]));
+            reinterpret_cast<uint4*>(dst)[i4] = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // dq_acc fp32 [rows, d] -> bf16 into dqkv[:, 0:d] (row pitch 3d)
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
                                        long long rows, int d) {
@@ -574,6 +796,19 @@ int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
   p.lse = const_cast<float*>(lse);
   p.o_in = (const __nv_bfloat16*)o; p.do_in = (const __nv_bfloat16*)d_o;
   p.dq_acc = (float*)workspace; p.dqkv = (__nv_bfloat16*)dqkv;
+  if (N <= 256 && g_debug[5] == 0) {
+    // short sequences: everything resident per (batch, head), no HBM accumulation
+    dim3 grid_small(H, B);
+    if (causal) {
+      B200_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmallSmem::TOTAL));
+      attn_bwd_small_kernel<true><<<grid_small, AT_THREADS, BwdSmallSmem::TOTAL, st>>>(tm_qkv, tm_do, p);
+    } else {
+      B200_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmallSmem::TOTAL));
+      attn_bwd_small_kernel<false><<<grid_small, AT_THREADS, BwdSmallSmem::TOTAL, st>>>(tm_qkv, tm_do, p);
+    }
+    B200_CUDA(cudaGetLastError());
+    return OK;
+  }
   B200_CUDA(cudaMemsetAsync(workspace, 0, b200vit_flash_attn_bwd_workspace_size(B, N, H), st));
   dim3 grid((N + AT_BK - 1) / AT_BK, H, B);
   if (causal) {
