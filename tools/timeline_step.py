@@ -1,0 +1,99 @@
+"""In-step kernel timeline of one ViT training step (warm caches, real launch order) via torch.profiler / CUPTI.
+
+    python tools/timeline_step.py [--batch 256] [--model B] [--steps 3] > profiles/rNN_timeline.md
+
+Prints per-kernel totals per step, the GPU busy time and the idle gaps between kernels.  nsys is not in the
+image; CUPTI activity records (what torch.profiler collects) see every kernel of the process, including the
+ones launched through the C ABI.
+"""
+import argparse
+import os
+import re
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "vit-is-all-you-need_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+from b200vit import modules as M  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--model", type=str, default="B")
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--dropout", type=float, default=0.0)
+args = ap.parse_args()
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+model = M.ViTClassifier(M.ViTConfig(224, 3, 16, args.model, 1, args.dropout), num_classes=1000).to(dev)
+optim = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2, fused=True)
+x = torch.randn(args.batch, 3, 224, 224, device=dev)
+y = torch.randint(0, 1000, (args.batch,), device=dev)
+
+
+def step():
+    optim.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = torch.nn.functional.cross_entropy(model(x).float(), y)
+    loss.backward()
+    optim.step()
+    return loss
+
+
+for _ in range(4):
+    step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(args.steps):
+    step()
+e1.record()
+torch.cuda.synchronize()
+plain_ms = e0.elapsed_time(e1) / args.steps
+
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+
+evs = []
+for e in prof.events():
+    if e.device_type == torch.autograd.DeviceType.CUDA:
+        evs.append((e.time_range.start, e.time_range.end, e.name))
+evs.sort()
+t_first, t_last = evs[0][0], max(e[1] for e in evs)
+busy = 0.0
+cur_s, cur_e = evs[0][0], evs[0][1]
+gaps = []
+for s, e, n in evs[1:]:
+    if s > cur_e:
+        busy += cur_e - cur_s
+        gaps.append((s - cur_e, n))
+        cur_s, cur_e = s, e
+    else:
+        cur_e = max(cur_e, e)
+busy += cur_e - cur_s
+agg = defaultdict(lambda: [0.0, 0])
+for s, e, n in evs:
+    short = re.sub(r"\(.*", "", n)
+    short = re.sub(r"^void ", "", short)
+    agg[short][0] += e - s
+    agg[short][1] += 1
+k = args.steps
+span = t_last - t_first
+print(f"# in-step kernel timeline: ViT-{args.model}/16 224 batch {args.batch}, {k} steps under torch.profiler (CUPTI)\n")
+print(f"* un-profiled step time (CUDA events): {plain_ms:.2f} ms")
+print(f"* profiled span per step: {span / k / 1e3:.2f} ms; GPU busy per step: {busy / k / 1e3:.2f} ms; "
+      f"idle (gaps between kernels) per step: {(span - busy) / k / 1e3:.2f} ms over {len(gaps) / k:.0f} gaps")
+big = sorted(gaps, reverse=True)[:8]
+print("* largest gaps (us, next kernel): " + "; ".join(f"{g:.0f} before {re.sub(r'[(<].*', '', n)[:40]}" for g, n in big))
+print("\n| kernel | launches/step | us/step | share of busy | avg us |")
+print("|---|---:|---:|---:|---:|")
+tot = sum(v[0] for v in agg.values())
+for name, (us, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+    print(f"| `{name[:100]}` | {n / k:.1f} | {us / k:.1f} | {100 * us / tot:.1f}% | {us / n:.1f} |")

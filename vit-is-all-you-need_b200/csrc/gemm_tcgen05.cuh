@@ -64,19 +64,33 @@ struct EpiParams {
 // GELU (exact erf form, nn.GELU() default) and its derivative from ONE exponential:
 //   erf(z) ~= 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1/(1 + p z)   (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7)
 // with z = |u| / sqrt(2), so exp(-z^2) = exp(-u^2 / 2) is also the Gaussian of the derivative.
+// The epilogue of the K=768 GEMMs has ~6100 tensor-pipe clocks per 128x256 tile to hide under, i.e. ~24 issue
+// slots per element with 8 epilogue warps, so this is written instruction by instruction (16 FP32-pipe ops +
+// 2 MUFU): with a = |u| and q = Phi(-a) = 0.5 erfc(a / sqrt 2) = (0.5 poly(t)) e,
+//   g  = u Phi(u)          = relu(u) - a q
+//   g' = Phi(u) + u phi(u) = 0.5 + copysign(0.5 - (q - a e / sqrt(2 pi)), u)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void gelu_and_grad(float u, float& g, float& gp) {
-  const float az = fabsf(u) * 0.70710678118654752f;
-  const float e = exp2f(-0.72134752044448170f * u * u);  // exp(-u^2/2)
-  const float t = __frcp_rn(fmaf(0.3275911f, az, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float cdf = 0.5f + 0.5f * copysignf(erf_abs, u);
-  g = u * cdf;
-  gp = fmaf(u * 0.39894228040143268f, e, cdf);
+  const float a = fabsf(u);
+  const float t = rcp_approx(fmaf(a, 0.3275911f * 0.70710678118654752f, 1.0f));
+  const float e = ex2_approx((u * u) * -0.72134752044448170f);  // exp(-u^2/2)
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  const float q = (poly * t) * e;
+  g = fmaf(-a, q, fmaxf(u, 0.0f));
+  const float w = fmaf(a * e, -0.39894228040143268f, q);
+  gp = 0.5f + copysignf(0.5f - w, u);
 }
 
 template <int BN, int KIND>
@@ -246,10 +260,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       const int t = w / s.splits;
       const int n0 = (t % s.tiles_n) * BN + half * (BN / 2);
       const int m0 = (t / s.tiles_n) * GEMM_BM + quarter * 32;
-      mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
-      tc_fence_after();
       const int row = m0 + lane;
       const bool row_ok = row < s.M;
+      // EPI_MUL_BF16: the multiplier tile does not depend on the accumulator -> fetch it one 32-column chunk
+      // ahead (registers), the first chunk before the accumulator is even complete
+      uint4 auxq[2][4];
+      auto load_aux = [&](int c, uint4 (&dst)[4]) {
+        const int col = n0 + c * 32;
+        const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)row * ep.ldaux + col;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = (row_ok && col + q * 8 < s.N) ? __ldg(reinterpret_cast<const uint4*>(a) + q) : make_uint4(0, 0, 0, 0);
+      };
+      if constexpr (KIND == EPI_MUL_BF16) load_aux(0, auxq[0]);
+      mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + half * (BN / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
       uint32_t vbuf[2][32];
       tmem_ld32(taddr, vbuf[0]);
@@ -257,6 +282,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       for (int c = 0; c < NCH; ++c) {
         tmem_ld_wait();
         if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
+        if constexpr (KIND == EPI_MUL_BF16) {
+          if (c + 1 < NCH) load_aux(c + 1, auxq[(c + 1) & 1]);
+        }
         const int col = n0 + c * 32;
         if (col < s.N) {  // warp-uniform
           float v[32];
@@ -319,17 +347,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           } else {
             // ---- bf16 output: a slab holds 64 columns = two chunks; store after the odd chunk ----
             if constexpr (KIND == EPI_MUL_BF16) {
-              if (row_ok) {
-                const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)row * ep.ldaux + col;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  if (col + q * 8 < s.N) {
-                    const uint4 uu = reinterpret_cast<const uint4*>(a)[q];
-                    const float2 a0 = unpack_bf16(uu.x), a1 = unpack_bf16(uu.y), a2 = unpack_bf16(uu.z), a3 = unpack_bf16(uu.w);
-                    v[q * 8 + 0] *= a0.x; v[q * 8 + 1] *= a0.y; v[q * 8 + 2] *= a1.x; v[q * 8 + 3] *= a1.y;
-                    v[q * 8 + 4] *= a2.x; v[q * 8 + 5] *= a2.y; v[q * 8 + 6] *= a3.x; v[q * 8 + 7] *= a3.y;
-                  }
-                }
+              for (int q = 0; q < 4; ++q) {
+                const uint4 uu = auxq[c & 1][q];
+                const float2 a0 = unpack_bf16(uu.x), a1 = unpack_bf16(uu.y), a2 = unpack_bf16(uu.z), a3 = unpack_bf16(uu.w);
+                v[q * 8 + 0] *= a0.x; v[q * 8 + 1] *= a0.y; v[q * 8 + 2] *= a1.x; v[q * 8 + 3] *= a1.y;
+                v[q * 8 + 4] *= a2.x; v[q * 8 + 5] *= a2.y; v[q * 8 + 6] *= a3.x; v[q * 8 + 7] *= a3.y;
               }
             }
             float gp[32];
