@@ -53,6 +53,10 @@ int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* gprime, 
 /* dw[N,K](f32) (+)= dy[M,N]^T x[M,K]                   autograd of nn.Linear wrt weight              */
 int b200vit_gemm_wgrad(const void* dy, const void* x, float* dw, int M, int N, int K, int accumulate,
                        void* stream);
+/* as above, plus db[N](f32) (+)= column sums of dy     autograd of nn.Linear wrt bias (transformer.py:21,37,39);
+ * summed inside the wgrad kernel from the shared-memory dy tiles, so dy is not read a second time       */
+int b200vit_gemm_wgrad_bias(const void* dy, const void* x, float* dw, float* db, int M, int N, int K,
+                            int accumulate, void* stream);
 
 /* ---- fused flash attention, head_dim 64 ----------------------------------------------------------------
  * qkv: [B, N, 3, H, 64] bf16 == the row-major output of the QKV Linear, "(qkv h d)" of transformer.py:27;

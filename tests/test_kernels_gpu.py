@@ -78,9 +78,60 @@ def test_gemm_dgrad_and_wgrad(ops, M, N, K):
     assert_close_bf16(dw2, 2 * dw_ref, "gemm_wgrad accumulate", rel=2e-5)
     db = ops.colsum_bf16(dyd)
     assert_close_bf16(db, dy.astype(np.float64).sum(0), "colsum_bf16", rel=2e-5)
+    # bias gradient fused into the wgrad kernel (column sums taken from the shared-memory dy tiles)
+    dw3, db3 = ops.gemm_wgrad(dyd, xd, want_bias=True)
+    assert_close_bf16(dw3, dw_ref, "gemm_wgrad_bias dw", rel=2e-5)
+    assert_close_bf16(db3, dy.astype(np.float64).sum(0), "gemm_wgrad_bias db", rel=2e-5)
+    dw4, db4 = ops.gemm_wgrad(dyd, xd, out=dw3.clone(), bias_out=db3.clone(), accumulate=True)
+    assert_close_bf16(dw4, 2 * dw_ref, "gemm_wgrad_bias accumulate dw", rel=2e-5)
+    assert_close_bf16(db4, 2 * dy.astype(np.float64).sum(0), "gemm_wgrad_bias accumulate db", rel=2e-5)
+
+
+def test_gemm_wgrad_bias_large(ops):
+    # many K-splits and several n-tiles per m-tile: every dy element must be counted exactly once
+    M, N, K = 9000, 2304, 768
+    rng = np.random.default_rng(5)
+    dy = bf16_round(rng.standard_normal((M, N)).astype(np.float32) * 0.1)
+    x = bf16_round(rng.standard_normal((M, K)).astype(np.float32) * 0.1)
+    dw, db = ops.gemm_wgrad(to_dev(dy, torch.bfloat16), to_dev(x, torch.bfloat16), want_bias=True)
+    assert_close_bf16(dw, dy.astype(np.float64).T @ x.astype(np.float64), "dw", rel=2e-5)
+    assert_close_bf16(db, dy.astype(np.float64).sum(0), "db", rel=2e-5)
 
 
 # ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("M,d,affine,with_add", [(197 * 5 + 3, 768, False, True), (197 * 5 + 3, 768, False, False),
+                                                 (301, 1024, True, True), (289 * 2, 512, True, False),
+                                                 (1029, 512, False, True)])
+def test_layernorm_specialised_kernels(ops, M, d, affine, with_add):
+    # the d = 512 / 768 / 1024 row kernels (bf16 output only, bwd without parameter gradients)
+    rng = np.random.default_rng(M + d + 1)
+    x = rng.standard_normal((M, d)).astype(np.float32) * 2 + 0.5
+    add = bf16_round(rng.standard_normal((M, d)).astype(np.float32))
+    gamma = (1 + 0.1 * rng.standard_normal(d)).astype(np.float32) if affine else None
+    beta = (0.1 * rng.standard_normal(d)).astype(np.float32) if affine else None
+    dy = bf16_round(rng.standard_normal((M, d)).astype(np.float32))
+    dres = rng.standard_normal((M, d)).astype(np.float32)
+    x1 = x + add if with_add else x
+    y_ref, cache = O.layer_norm_fwd(x1.astype(np.float64), None if gamma is None else gamma.astype(np.float64),
+                                    None if beta is None else beta.astype(np.float64))
+    dx_ref, _, _ = O.layer_norm_bwd(dy.astype(np.float64), cache)
+    gd = None if gamma is None else to_dev(gamma)
+    bd = None if beta is None else to_dev(beta)
+    y, _, mean, rstd, x_out = ops.layernorm_fwd(to_dev(x), add=to_dev(add, torch.bfloat16) if with_add else None,
+                                                gamma=gd, beta=bd, want_x_out=with_add)
+    if with_add:
+        assert_close_bf16(x_out, x1, "x + add", rel=1e-6)
+    assert_close_bf16(y, y_ref, "LN fwd bf16", rel=5e-3)
+    assert_close_bf16(mean, x1.astype(np.float64).mean(-1), "mean", rel=1e-5)
+    assert_close_bf16(rstd, 1.0 / np.sqrt(x1.astype(np.float64).var(-1) + 1e-5), "rstd", rel=1e-5)
+    for use_dres in (True, False):
+        dx, dxb, _, _ = ops.layernorm_bwd(to_dev(dy, torch.bfloat16), to_dev(x1.astype(np.float32)), mean, rstd, gamma=gd,
+                                          dres=to_dev(dres) if use_dres else None, want_bf16=True)
+        ref = dx_ref + dres if use_dres else dx_ref
+        assert_close_bf16(dx, ref, "LN bwd dx", rel=2e-5)
+        assert_close_bf16(dxb, ref, "LN bwd dx bf16", rel=5e-3)
+
+
 @pytest.mark.parametrize("M,d,affine", [(65 * 4, 192, False), (197 * 3, 768, False), (100, 1024, True), (289 * 2, 512, True), (7, 64, False)])
 def test_layernorm_fwd_bwd(ops, M, d, affine):
     rng = np.random.default_rng(M + d)

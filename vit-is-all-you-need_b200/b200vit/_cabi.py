@@ -47,6 +47,7 @@ _SIGNATURES = {
     "b200vit_gemm_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "b200vit_gemm_dgrad_dgelu": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "b200vit_gemm_wgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200vit_gemm_wgrad_bias": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200vit_flash_attn_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200vit_flash_attn_bwd_workspace_size": (_Z, [_I, _I, _I]),
     "b200vit_flash_attn_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),

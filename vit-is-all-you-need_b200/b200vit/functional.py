@@ -95,18 +95,15 @@ def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_d
     """dx2: [B*N, d] fp32 (dx2_bf16: optional bf16 copy).  Returns (dx0, dx0_bf16, grads in LayerParams order)."""
     x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g = saved
     dv = dx2_bf16 if dx2_bf16 is not None else ops.cast_bf16(dx2)
-    d_fc2_w = ops.gemm_wgrad(dv, g, out=_slot(P.fc2_w))
-    d_fc2_b = ops.colsum_bf16(dv, out=_slot(P.fc2_b))
+    d_fc2_w, d_fc2_b = ops.gemm_wgrad(dv, g, out=_slot(P.fc2_w), bias_out=_slot(P.fc2_b), want_bias=True)
     _ready(P.fc2_w, P.fc2_b)
     du = ops.gemm_dgrad_dgelu(dv, bf16_of(P.fc2_w), u)
-    d_fc1_w = ops.gemm_wgrad(du, b, out=_slot(P.fc1_w))
-    d_fc1_b = ops.colsum_bf16(du, out=_slot(P.fc1_b))
+    d_fc1_w, d_fc1_b = ops.gemm_wgrad(du, b, out=_slot(P.fc1_w), bias_out=_slot(P.fc1_b), want_bias=True)
     _ready(P.fc1_w, P.fc1_b)
     db = ops.gemm_dgrad(du, bf16_of(P.fc1_w))
     dx1, dx1_bf16, _, _ = ops.layernorm_bwd(db, x1, mean2, rstd2, dres=dx2, want_bf16=True)
     dqkv = ops.flash_attn_bwd(qkv, o, dx1_bf16.view(B, N, -1), lse, B, N, H, causal).view(B * N, -1)
-    d_qkv_w = ops.gemm_wgrad(dqkv, a, out=_slot(P.qkv_w))
-    d_qkv_b = ops.colsum_bf16(dqkv, out=_slot(P.qkv_b))
+    d_qkv_w, d_qkv_b = ops.gemm_wgrad(dqkv, a, out=_slot(P.qkv_w), bias_out=_slot(P.qkv_b), want_bias=True)
     _ready(P.qkv_w, P.qkv_b)
     dx0 = dx0_bf16 = None
     if need_dx:
@@ -175,8 +172,7 @@ class AttentionFn(torch.autograd.Function):
         B, N, d, H, causal = ctx.dims
         do16 = ops.cast_bf16(_as_rows_f32(do).view(B * N, d)).view(B, N, d)
         dqkv = ops.flash_attn_bwd(qkv, o, do16, lse, B, N, H, causal).view(B * N, -1)
-        dw = ops.gemm_wgrad(dqkv, a)
-        db = ops.colsum_bf16(dqkv)
+        dw, db = ops.gemm_wgrad(dqkv, a, want_bias=True)
         dx = ops.gemm_dgrad(dqkv, bf16_of(qkv_w)).float().view(B, N, d)
         return dx, dw, db, None, None
 
@@ -256,23 +252,19 @@ class ResidualAttentionBlockFn(torch.autograd.Function):
             mean2, rstd2, b, u, g = s[8:]
             ln2_w, _, fc_w, _, proj_w, _ = ctx.params[3:]
             dv = ops.cast_bf16(dx2)
-            d_proj_w = ops.gemm_wgrad(dv, g)
-            d_proj_b = ops.colsum_bf16(dv)
+            d_proj_w, d_proj_b = ops.gemm_wgrad(dv, g, want_bias=True)
             du = ops.gemm_dgrad_dgelu(dv, bf16_of(proj_w), u)
-            d_fc_w = ops.gemm_wgrad(du, b)
-            d_fc_b = ops.colsum_bf16(du)
+            d_fc_w, d_fc_b = ops.gemm_wgrad(du, b, want_bias=True)
             db = ops.gemm_dgrad(du, bf16_of(fc_w))
             dx1, dx1_16, d_ln2_w, d_ln2_b = ops.layernorm_bwd(db, x1, mean2, rstd2, gamma=_f32c(ln2_w), dres=dx2,
                                                               want_bf16=True, affine_grads=True)
             mlp_grads = (d_ln2_w, d_ln2_b, d_fc_w, d_fc_b, d_proj_w, d_proj_b)
         else:
             dx1, dx1_16 = dx2, ops.cast_bf16(dx2)
-        d_out_w = ops.gemm_wgrad(dx1_16, o.view(M, d))
-        d_out_b = ops.colsum_bf16(dx1_16)
+        d_out_w, d_out_b = ops.gemm_wgrad(dx1_16, o.view(M, d), want_bias=True)
         do = ops.gemm_dgrad(dx1_16, bf16_of(out_w))
         dqkv = ops.flash_attn_bwd(qkv, o, do.view(L, B, d), lse, B, L, H, False, seq_first=True).view(M, -1)
-        d_in_w = ops.gemm_wgrad(dqkv, a)
-        d_in_b = ops.colsum_bf16(dqkv)
+        d_in_w, d_in_b = ops.gemm_wgrad(dqkv, a, want_bias=True)
         da = ops.gemm_dgrad(dqkv, bf16_of(in_w))
         dx0, _, d_ln1_w, d_ln1_b = ops.layernorm_bwd(da, x0, mean1, rstd1, gamma=_f32c(ln1_w), dres=dx1,
                                                      want_bf16=False, affine_grads=True)

@@ -122,7 +122,9 @@ def gemm_dgrad_dgelu(dy, w, gprime):
     return dx
 
 
-def gemm_wgrad(dy, x, out=None, accumulate=False):
+def gemm_wgrad(dy, x, out=None, accumulate=False, bias_out=None, want_bias=False):
+    """dw[N,K] = dy^T x (fp32).  With want_bias (or bias_out) also returns db[N] = column sums of dy, summed inside
+    the same kernel from the shared-memory dy tiles (no second pass over dy)."""
     M, N = dy.shape
     K = x.shape[1]
     if out is None:
@@ -130,8 +132,13 @@ def gemm_wgrad(dy, x, out=None, accumulate=False):
         accumulate = False
     elif tuple(out.shape) != (N, K):
         out = out.view(N, K)
-    _call("b200vit_gemm_wgrad", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(x, BF16, "x")), ptr(_chk(out, F32, "dw")), M, N, K, 1 if accumulate else 0, stream_ptr(), flops=2.0 * M * N * K)
-    return out
+    if bias_out is None and want_bias:
+        bias_out = torch.empty(N, device=dy.device, dtype=F32)
+    if bias_out is None:
+        _call("b200vit_gemm_wgrad", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(x, BF16, "x")), ptr(_chk(out, F32, "dw")), M, N, K, 1 if accumulate else 0, stream_ptr(), flops=2.0 * M * N * K)
+        return out
+    _call("b200vit_gemm_wgrad_bias", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(x, BF16, "x")), ptr(_chk(out, F32, "dw")), ptr(_chk(bias_out, F32, "db")), M, N, K, 1 if accumulate else 0, stream_ptr(), flops=2.0 * M * N * K)
+    return out, bias_out
 
 
 # ---------------------------------------------------------------- attention

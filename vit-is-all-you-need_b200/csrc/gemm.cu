@@ -93,7 +93,7 @@ static int check_common(const void* a, const void* b, const void* c, int M, int 
 static EpiParams make_ep(void* out, long long ldo) {
   EpiParams ep;
   ep.out = out; ep.ldo = ldo; ep.bias = nullptr;
-  ep.aux = nullptr; ep.ldaux = 0; ep.pos = nullptr; ep.P = 1; ep.T = 1; ep.extra = 0;
+  ep.aux = nullptr; ep.ldaux = 0; ep.pos = nullptr; ep.P = 1; ep.T = 1; ep.extra = 0; ep.colsum = nullptr;
   return ep;
 }
 
@@ -170,15 +170,25 @@ int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* gprime, 
 }
 
 // dw[N,K] = dy[M,N]^T x[M,K]: output rows = N, output cols = K, contraction over M (split-K).
-int b200vit_gemm_wgrad(const void* dy, const void* x, float* dw, int M, int N, int K, int accumulate,
-                       void* stream) {
+// db[N] (optional) = column sums of dy, accumulated by two otherwise idle warps from the smem dy tiles.
+int b200vit_gemm_wgrad_bias(const void* dy, const void* x, float* dw, float* db, int M, int N, int K,
+                            int accumulate, void* stream) {
   int rc = check_common(dy, x, dw, M, N, K);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   EpiParams ep = make_ep(dw, K);
-  if (!accumulate) B200_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+  ep.colsum = db;
+  if (!accumulate) {
+    B200_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+    if (db) B200_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, st));
+  }
   return launch_bn<true, true, EPI_ATOMIC_F32>(dy, N, x, K, /*M_out=*/N, /*N_out=*/K,
                                                /*K_contract=*/M, ep, true, st);
+}
+
+int b200vit_gemm_wgrad(const void* dy, const void* x, float* dw, int M, int N, int K, int accumulate,
+                       void* stream) {
+  return b200vit_gemm_wgrad_bias(dy, x, dw, nullptr, M, N, K, accumulate, stream);
 }
 
 }  // extern "C"

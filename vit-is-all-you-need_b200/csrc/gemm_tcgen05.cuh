@@ -59,6 +59,7 @@ struct EpiParams {
   long long ldaux;
   const float* pos;  // [P, N] fp32
   int P, T, extra;
+  float* colsum;     // wgrad only: colsum[m] += sum_k A(m, k)  (= bias gradient, summed from the smem A tiles)
 };
 
 // GELU (exact erf form, nn.GELU() default) and its derivative from ONE exponential:
@@ -150,6 +151,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool do_colsum = A_MN && KIND == EPI_ATOMIC_F32 && ep.colsum != nullptr;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
@@ -158,7 +160,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (KIND == EPI_GELU_BF16) tma_prefetch_desc(&tma_out2);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], do_colsum ? 3 : 1);  // MMA commit (+ the two column-sum warps)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -244,6 +246,61 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 4 && do_colsum) {
+    // ------------------- bias gradient: column sums of dy straight from the smem A tiles -------------------
+    // wgrad: A = dy stored [K = rows of dy][MN = columns of dy]; a stage holds two 64(K) x 64(MN) boxes whose
+    // rows are 128 B with the 16-byte chunks XOR-swizzled by (row & 7).  Warp 2 sums box 0, warp 3 box 1:
+    // lane = (row group rg = lane / 8, chunk j = lane % 8); each LDS.128 of the warp covers 4 full rows.
+    // Only the first n-tile of every (m-tile, split) adds, so each dy element is counted exactly once.
+    if constexpr (A_MN && KIND == EPI_ATOMIC_F32) {
+      const int box = warp - 2;
+      const int j = lane & 7, rg = lane >> 3;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < s.total_work; w += gridDim.x) {
+        const int split = w % s.splits;
+        const int t = w / s.splits;
+        const bool mine = (t % s.tiles_n) == 0;
+        const int m0 = (t / s.tiles_n) * GEMM_BM + box * 64;
+        const int kb0 = split * s.kb_per;
+        const int kb1 = min(s.kb_total, kb0 + s.kb_per);
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 500 + stage);
+          if (mine) {
+            const uint8_t* sa = smem + stage * Cfg::STAGE_BYTES + box * 8192;
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+              const int r = it * 4 + rg;
+              const uint4 q = *reinterpret_cast<const uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4));
+              acc[0] += __uint_as_float(q.x << 16); acc[1] += __uint_as_float(q.x & 0xffff0000u);
+              acc[2] += __uint_as_float(q.y << 16); acc[3] += __uint_as_float(q.y & 0xffff0000u);
+              acc[4] += __uint_as_float(q.z << 16); acc[5] += __uint_as_float(q.z & 0xffff0000u);
+              acc[6] += __uint_as_float(q.w << 16); acc[7] += __uint_as_float(q.w & 0xffff0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (mine) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+          }
+          if (rg == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int m = m0 + j * 8 + e;
+              if (m < s.M) atomicAdd(ep.colsum + m, acc[e]);
+            }
+          }
+        }
       }
     }
   } else if (warp >= 4) {
