@@ -40,6 +40,7 @@ _SIGNATURES = {
     "b200vit_init": (_I, [_I]),
     "b200vit_version": (_I, []),
     "b200vit_debug_set": (_I, [_I, _I]),
+    "b200vit_debug_max_clusters": (_I, []),
     "b200vit_gemm_bias": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "b200vit_gemm_bias_gelu": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "b200vit_gemm_bias_residual": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),

@@ -4,19 +4,18 @@
 
 namespace b200 {
 
-// Pick the K-split that minimises (waves x k-blocks per work item) on a persistent grid.
-static void plan_splits(GemmShape& s, bool allow_split) {
+// Pick the K-split that minimises (waves x k-blocks per work item) on a persistent grid of `workers` CTAs / CTA pairs.
+static void plan_splits(GemmShape& s, bool allow_split, int workers) {
   const int tiles = s.tiles_m * s.tiles_n;
-  const int sms = num_sms();
   int best_splits = 1;
-  if (allow_split && tiles < sms) {
+  if (allow_split && tiles < workers) {
     double best_cost = 1e30;
     const int max_splits = s.kb_total < 64 ? s.kb_total : 64;
     for (int sp = 1; sp <= max_splits; ++sp) {
       const int kb_per = (s.kb_total + sp - 1) / sp;
       const int eff = (s.kb_total + kb_per - 1) / kb_per;  // non-empty splits
       if (eff != sp) continue;
-      const int waves = (tiles * sp + sms - 1) / sms;
+      const int waves = (tiles * sp + workers - 1) / workers;
       const double cost = (double)waves * (kb_per + 8.0);  // +8: prologue/epilogue per work item
       if (cost < best_cost) { best_cost = cost; best_splits = sp; }
     }
@@ -26,19 +25,21 @@ static void plan_splits(GemmShape& s, bool allow_split) {
   s.total_work = tiles * s.splits;
 }
 
-template <bool A_MN, bool B_MN, int BN, int KIND>
+template <bool A_MN, bool B_MN, int BN, int KIND, int NCTA>
 static int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                   const EpiParams& ep, void* out2, bool allow_split, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, KIND>;
+  using Cfg = GemmCfg<BN, KIND, NCTA>;
   GemmShape s;
   s.M = M; s.N = N; s.K = K;
-  s.tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+  s.tiles_m = (M + GEMM_BM * NCTA - 1) / (GEMM_BM * NCTA);
   s.tiles_n = (N + BN - 1) / BN;
   s.kb_total = (K + GEMM_BK - 1) / GEMM_BK;
   s.mn_lbo = g_debug[0] ? g_debug[0] : 8192;
   s.mn_sbo = g_debug[1] ? g_debug[1] : 1024;
   s.mn_kadv = g_debug[2] ? g_debug[2] : 2048;
-  plan_splits(s, allow_split);
+  int workers = num_sms() / NCTA;
+  if (g_debug[3] > 0 && workers > g_debug[3]) workers = g_debug[3];
+  plan_splits(s, allow_split, workers);
 
   CUtensorMap ta, tb;
   int rc;
@@ -46,7 +47,7 @@ static int launch(const void* A, long long lda, const void* B, long long ldb, in
   else      rc = make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM, 64);
   if (rc != OK) return rc;
   if (B_MN) rc = make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 64);
-  else      rc = make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, 64);
+  else      rc = make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, Cfg::B_ROWS, 64);
   if (rc != OK) return rc;
 
   // output tensor maps for the TMA-store epilogue (32-row slabs of 128 bytes)
@@ -61,26 +62,40 @@ static int launch(const void* A, long long lda, const void* B, long long ldb, in
     }
   }
 
-  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, KIND>;
+  auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, KIND, NCTA>;
   static bool attr_done = false;  // per instantiation
   if (!attr_done) {
     B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  int grid = s.total_work < num_sms() ? s.total_work : num_sms();
-  if (g_debug[3] > 0 && grid > g_debug[3]) grid = g_debug[3];
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, to, to2, s, ep);
-  B200_CUDA(cudaGetLastError());
+  const int nwork = s.total_work < workers ? s.total_work : workers;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nwork * NCTA);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, s, ep));
   return OK;
 }
 
 template <bool A_MN, bool B_MN, int KIND>
 static int launch_bn(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                      const EpiParams& ep, bool allow_split, cudaStream_t st, void* out2 = nullptr) {
-  // 128x256 tiles when N fills them; 128x128 otherwise (less padding waste for narrow outputs).
+  // 256-wide N tiles when N fills them; 128 otherwise (less padding waste for narrow outputs).
   const bool wide = (g_debug[4] == 256) || (g_debug[4] != 128 && (N % 256 == 0 || N >= 1024));
-  if (wide) return launch<A_MN, B_MN, 256, KIND>(A, lda, B, ldb, M, N, K, ep, out2, allow_split, st);
-  return launch<A_MN, B_MN, 128, KIND>(A, lda, B, ldb, M, N, K, ep, out2, allow_split, st);
+  // CTA pairs (256-row tiles, cta_group::2) whenever there is more than one 128-row tile of output.
+  const bool pair = (g_debug[5] == 2) || (g_debug[5] != 1 && M > GEMM_BM);
+  if (pair) {
+    if (wide) return launch<A_MN, B_MN, 256, KIND, 2>(A, lda, B, ldb, M, N, K, ep, out2, allow_split, st);
+    return launch<A_MN, B_MN, 128, KIND, 2>(A, lda, B, ldb, M, N, K, ep, out2, allow_split, st);
+  }
+  if (wide) return launch<A_MN, B_MN, 256, KIND, 1>(A, lda, B, ldb, M, N, K, ep, out2, allow_split, st);
+  return launch<A_MN, B_MN, 128, KIND, 1>(A, lda, B, ldb, M, N, K, ep, out2, allow_split, st);
 }
 
 static int check_common(const void* a, const void* b, const void* c, int M, int N, int K) {
@@ -111,6 +126,25 @@ int gemm_patch_epilogue(const void* xcol, const void* w, const float* bias, cons
 using namespace b200;
 
 extern "C" {
+
+// bring-up aid: how many CTA pairs of the forward GEMM kernel can be co-resident on this device
+int b200vit_debug_max_clusters(void) {
+  using Cfg = GemmCfg<256, EPI_BF16, 2>;
+  auto kern = gemm_tcgen05_kernel<false, false, 256, EPI_BF16, 2>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess) return -1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_sms());
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) return -2;
+  return n;
+}
 
 int b200vit_gemm_bias(const void* x, const void* w, const float* bias, void* y, int M, int N, int K,
                       void* stream) {

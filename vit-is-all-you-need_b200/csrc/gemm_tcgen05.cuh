@@ -16,6 +16,16 @@
 // Warp roles (384 threads, 1 CTA/SM): warp0 = TMA producer, warp1 = MMA issuer (one thread),
 // warp2 = TMEM allocator, warps 4..11 = epilogue.  Epilogue warp e owns TMEM lanes 32*(e%4).. (32 output rows)
 // and the column half e/4 of the tile, so two warps share each lane quarter.
+//
+// NCTA = 2 (the default for large problems) runs the same roles on a CTA PAIR (cluster of 2, one TPC): the pair owns
+// a 256 x BN tile, each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), and the leader CTA's
+// single thread issues tcgen05.mma.cta_group::2 (M = 256) that reads both CTAs' shared memory and writes each
+// CTA's half of the accumulator into that CTA's own TMEM.  Per SM this moves 2/3 of the bytes of the 1-CTA
+// 128 x 256 tile from L2 and reads 2/3 of the bytes from shared memory per MMA, which is what bounds the
+// 1-CTA kernel (B300_MICROARCH: ~42 B/clk/SM from L2).  Synchronisation across the pair: every CTA's TMA signals
+// its OWN full barrier; in the non-leader CTA a relay thread forwards each "stage full" to the leader's barrier
+// (remote mbarrier.arrive, release.cluster); tcgen05.commit multicasts "stage free" / "accumulator ready" to
+// both CTAs; both CTAs' epilogue warps arrive on the leader's "accumulator drained" barrier.
 #pragma once
 #include "common.cuh"
 
@@ -94,10 +104,61 @@ __device__ __forceinline__ void gelu_and_grad(float u, float& g, float& gp) {
   gp = 0.5f + copysignf(0.5f - w, u);
 }
 
-template <int BN, int KIND>
+// ---- CTA-pair (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a location in this CTA's shared memory) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+// Remote arrive with the default (.release.cta) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id) does: a
+// .release.cluster arrive compiles to MEMBAR.ALL.GPU (~1 us) and would serialise the relay at one stage per us.
+// What is being published was written by the async proxy (TMA, complete_tx on the local barrier) or read through
+// tcgen05.ld + tcgen05.fence, neither of which needs a generic-proxy cluster fence.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all earlier cta_group::2 MMAs arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
+template <int BN, int KIND, int NCTA = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;       // 32 KB (BN=256) / 16 KB (BN=128)
+  static constexpr int B_ROWS = BN / NCTA;               // B-tile rows staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;   // 1 CTA: 32 KB (BN=256) / 16 KB (BN=128); CTA pair: half
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int SLABS = (KIND == EPI_GELU_BF16) ? 2 : 1;  // staging slabs (32 rows x 128 B) per epilogue warp
   static constexpr int EPI_BYTES = GEMM_EPI_WARPS * SLABS * 4096;
@@ -130,14 +191,18 @@ __device__ __forceinline__ uint4* slab_chunk(uint8_t* slab, int r, int j) {
   return reinterpret_cast<uint4*>(slab + r * 128 + ((j ^ (r & 7)) << 4));
 }
 
-template <bool A_MN, bool B_MN, int BN, int KIND>
+template <bool A_MN, bool B_MN, int BN, int KIND, int NCTA = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                     const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_out2,
                     const GemmShape s, const EpiParams ep) {
-  using Cfg = GemmCfg<BN, KIND>;
+  using Cfg = GemmCfg<BN, KIND, NCTA>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr bool OUT_F32 = epi_out_is_f32(KIND);
+  constexpr int TILE_M = GEMM_BM * NCTA;  // rows of the (pair's) output tile
+  const uint32_t cta_rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int worker = blockIdx.x / NCTA, nworkers = gridDim.x / NCTA;  // persistent work distribution (per pair)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -159,21 +224,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (KIND != EPI_PATCH_F32) tma_prefetch_desc(&tma_out);
     if (KIND == EPI_GELU_BF16) tma_prefetch_desc(&tma_out2);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], (NCTA == 2 && leader) ? 2 : 1);  // own producer (+ the peer's relay)
       mbar_init(&empty_bar[i], do_colsum ? 3 : 1);  // MMA commit (+ the two column-sum warps)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], GEMM_EPI_WARPS * NCTA);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (NCTA == 2) { tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish_2cta(); }
+    else                     { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -182,11 +247,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < s.total_work; w += gridDim.x) {
+      for (int w = worker; w < s.total_work; w += nworkers) {
         const int split = w % s.splits;
         const int t = w / s.splits;
-        const int n0 = (t % s.tiles_n) * BN;
-        const int m0 = (t / s.tiles_n) * GEMM_BM;
+        const int n0 = (t % s.tiles_n) * BN + cta_rank * Cfg::B_ROWS;  // this CTA's slice of the B tile
+        const int m0 = (t / s.tiles_n) * TILE_M + cta_rank * GEMM_BM;
         const int kb0 = split * s.kb_per;
         const int kb1 = min(s.kb_total, kb0 + s.kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -204,7 +269,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           }
           if constexpr (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
+            for (int i = 0; i < Cfg::B_ROWS / 64; ++i)
               tma_load_2d(sb + i * 8192, &tma_b, &full_bar[stage], n0 + i * 64, k0);
           } else {
             tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
@@ -214,14 +279,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+    // ------------------------------- MMA issuer (leader CTA only) ---------------
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int w = blockIdx.x; w < s.total_work; w += gridDim.x) {
+      for (int w = worker; w < s.total_work; w += nworkers) {
         const int split = w % s.splits;
         const int kb0 = split * s.kb_per;
         const int kb1 = min(s.kb_total, kb0 + s.kb_per);
@@ -239,13 +304,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                      : umma_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_smem_desc(sb + k * s.mn_kadv, s.mn_lbo, s.mn_sbo)
                                      : umma_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (NCTA == 2) umma_bf16_2cta(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else                     umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs) once these MMAs have read it
+          if constexpr (NCTA == 2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (NCTA == 2) umma_commit_2cta(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (NCTA == 2 && warp == 2 && !leader && !do_colsum) {
+    // ------------------- relay: this CTA's "stage full" -> the leader's full barrier ------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = worker; w < s.total_work; w += nworkers) {
+        const int split = w % s.splits;
+        const int kb0 = split * s.kb_per;
+        const int kb1 = min(s.kb_total, kb0 + s.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 600 + stage);
+          mbar_arrive_cluster(mapa_shared(&full_bar[stage], 0));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp < 4 && do_colsum) {
@@ -253,17 +337,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // wgrad: A = dy stored [K = rows of dy][MN = columns of dy]; a stage holds two 64(K) x 64(MN) boxes whose
     // rows are 128 B with the 16-byte chunks XOR-swizzled by (row & 7).  Warp 2 sums box 0, warp 3 box 1:
     // lane = (row group rg = lane / 8, chunk j = lane % 8); each LDS.128 of the warp covers 4 full rows.
-    // Only the first n-tile of every (m-tile, split) adds, so each dy element is counted exactly once.
+    // The n-tiles of an m-tile see the same dy tiles; k-block kb is summed by n-tile (kb mod tiles_n) only, so each
+    // dy element is counted exactly once and the extra shared-memory reads are spread evenly over all work items.
     if constexpr (A_MN && KIND == EPI_ATOMIC_F32) {
       const int box = warp - 2;
       const int j = lane & 7, rg = lane >> 3;
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < s.total_work; w += gridDim.x) {
+      for (int w = worker; w < s.total_work; w += nworkers) {
         const int split = w % s.splits;
         const int t = w / s.splits;
-        const bool mine = (t % s.tiles_n) == 0;
-        const int m0 = (t / s.tiles_n) * GEMM_BM + box * 64;
+        const int nt = t % s.tiles_n;  // the n-tiles of an m-tile share the k-blocks: tile nt sums kb % tiles_n == nt
+        const int m0 = (t / s.tiles_n) * TILE_M + cta_rank * GEMM_BM + box * 64;
         const int kb0 = split * s.kb_per;
         const int kb1 = min(s.kb_total, kb0 + s.kb_per);
         float acc[8];
@@ -271,7 +356,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int e = 0; e < 8; ++e) acc[e] = 0.f;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase, 500 + stage);
-          if (mine) {
+          if constexpr (NCTA == 2) {  // non-leader: warp 2 doubles as the relay to the leader's full barrier
+            if (!leader && warp == 2 && lane == 0) mbar_arrive_cluster(mapa_shared(&full_bar[stage], 0));
+          }
+          if (kb % s.tiles_n == nt) {
             const uint8_t* sa = smem + stage * Cfg::STAGE_BYTES + box * 8192;
 #pragma unroll
             for (int it = 0; it < 16; ++it) {
@@ -287,7 +375,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           if (lane == 0) mbar_arrive(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (mine) {
+        {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
@@ -313,10 +401,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     uint8_t* slab1 = slab0 + 4096;  // GELU kind only
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < s.total_work; w += gridDim.x) {
+    const uint32_t tmem_empty_leader0 = NCTA == 2 ? mapa_shared(&tmem_empty[0], 0) : 0u;
+    const uint32_t tmem_empty_leader1 = NCTA == 2 ? mapa_shared(&tmem_empty[1], 0) : 0u;
+    for (int w = worker; w < s.total_work; w += nworkers) {
       const int t = w / s.splits;
       const int n0 = (t % s.tiles_n) * BN + half * (BN / 2);
-      const int m0 = (t / s.tiles_n) * GEMM_BM + quarter * 32;
+      const int m0 = (t / s.tiles_n) * TILE_M + cta_rank * GEMM_BM + quarter * 32;
       const int row = m0 + lane;
       const bool row_ok = row < s.M;
       // EPI_MUL_BF16: the multiplier tile does not depend on the accumulator -> fetch it one 32-column chunk
@@ -447,17 +537,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (NCTA == 2) mbar_arrive_cluster(acc == 0 ? tmem_empty_leader0 : tmem_empty_leader1);
+        else                     mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if constexpr (NCTA == 2) tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+    else                     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
