@@ -289,6 +289,276 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
 }
 
 // --------------------------------------------------------------------------------------------------
+// Forward for short sequences (N <= 256, no causal mask: the ViT token counts 65 / 197 and every other
+// encoder of the reference whose sequence fits two 128-row tiles).  Persistent, one CTA per SM, a work unit is
+// one (batch, head):
+//   * Q, K, V of the whole head are staged once per unit (TMA, 2-deep ring: the next unit's tiles land while
+//     this one computes);
+//   * the score rows of a 128-query tile fit TMEM completely (<= 256 fp32 columns), so softmax is exact and
+//     single-shot: no running max, no rescaling of O, no second key block;
+//   * P is written back to TMEM as packed bf16 over the dead S columns and consumed by the tensor core directly
+//     (tcgen05.mma with the A operand in TMEM), so it never touches shared memory;
+//   * two warpgroups own the two query tiles (TMEM columns [0,256) and [256,512)), so one tile's softmax overlaps
+//     the other tile's MMAs.
+// TMEM columns of tile t (base 256 t): S fp32 [0, ncols), P bf16 [0, ncols/2) (overwrites S behind the reads),
+// O fp32 [128, 192) (S is dead by then).
+// --------------------------------------------------------------------------------------------------
+constexpr int AS_THREADS = 384;  // warp 0: TMA, warp 1: MMA issue, warp 2: TMEM alloc, warps 4-7 / 8-11: softmax of query tile 0 / 1
+struct FwdShortSmem {
+  static constexpr int STAGE = 6 * AT_TILE_BYTES;          // Q0 Q1 | K (256 rows) | V (256 rows) = 96 KB
+  static constexpr int Q = 0, K = 2 * AT_TILE_BYTES, V = 4 * AT_TILE_BYTES;
+  static constexpr int BAR = 2 * STAGE;
+  static constexpr int TOTAL = BAR + 256;
+};
+
+__device__ __forceinline__ void tmem_st16_packed(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st16(taddr, v); }
+
+__global__ void __launch_bounds__(AS_THREADS, 1)
+attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t at_smem_raw[];
+  uint8_t* smem = at_smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdShortSmem::BAR);
+  uint64_t* full = bars + 0;      // [2] stage loaded (TMA tx)
+  uint64_t* empty = bars + 2;     // [2] stage consumed (MMA commit)
+  uint64_t* s_full = bars + 4;    // [2] S of tile t complete (MMA commit)
+  uint64_t* p_ready = bars + 6;   // [2] P of tile t in TMEM (4 warp arrivals)
+  uint64_t* o_full = bars + 8;    // [2] O of tile t complete (MMA commit)
+  uint64_t* o_free = bars + 10;   // [2] O of tile t read out (4 warp arrivals) -> TMEM columns reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = p.B * p.H;
+  const int ntiles = (p.N + 127) >> 7;                 // 1 or 2 query tiles
+  const int ncols = ((p.N + 15) >> 4) << 4;            // S columns = keys padded to the MMA N granularity
+  const int kv_boxes = (p.N + 127) >> 7;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4);
+      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
+        const int st = n & 1;
+        const int b = u / p.H, hh = u - b * p.H;
+        mbar_wait(&empty[st], ((n >> 1) & 1) ^ 1, 40);
+        uint8_t* base = smem + st * FwdShortSmem::STAGE;
+        mbar_expect_tx(&full[st], (ntiles + 2 * kv_boxes) * AT_TILE_BYTES);
+        for (int t = 0; t < kv_boxes; ++t) {  // K first: the S MMAs need Q and K, V only later
+          tma_load_3d(base + FwdShortSmem::K + t * AT_TILE_BYTES, &tm_qkv, &full[st], p.d + hh * AT_HD, t * 128, b);
+        }
+        for (int t = 0; t < ntiles; ++t)
+          tma_load_3d(base + FwdShortSmem::Q + t * AT_TILE_BYTES, &tm_qkv, &full[st], hh * AT_HD, t * 128, b);
+        for (int t = 0; t < kv_boxes; ++t)
+          tma_load_3d(base + FwdShortSmem::V + t * AT_TILE_BYTES, &tm_qkv, &full[st], 2 * p.d + hh * AT_HD, t * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, ncols, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, AT_HD, false, true);
+      const int ksteps = ncols >> 4;
+      // Issue order in steady state: S0(n), PV1(n-1), S1(n), PV0(n).  The two warpgroups then run half a period
+      // apart, so one tile's softmax (MUFU-bound) overlaps the other tile's PV MMA, O read-out and hand-offs.
+      // (One issuing thread per tile was measured slower: the warpgroups fall into lock-step and share the MUFU.)
+      auto issue_s = [&](int n, int t) {
+        const uint32_t sbase = smem_u32(smem + (n & 1) * FwdShortSmem::STAGE);
+        const uint32_t sQ = sbase + FwdShortSmem::Q + t * AT_TILE_BYTES, sK = sbase + FwdShortSmem::K;
+        mbar_wait(&o_free[t], (n & 1) ^ 1, 42);  // previous unit's O (same TMEM columns) has been read
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + t * 256, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int n, int t) {
+        const uint32_t sV = smem_u32(smem + (n & 1) * FwdShortSmem::STAGE) + FwdShortSmem::V;
+        mbar_wait(&p_ready[t], n & 1, 43);
+        tc_fence_after();
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + k * 8, desc_mnmajor(sV, k, 8192), idesc_o, k > 0);
+        umma_commit(&o_full[t]);
+      };
+      int n = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
+        mbar_wait(&full[n & 1], (n >> 1) & 1, 41);
+        issue_s(n, 0);
+        if (ntiles == 2) {
+          if (n > 0) { issue_pv(n - 1, 1); umma_commit(&empty[(n - 1) & 1]); }  // stage n-1 fully consumed
+          issue_s(n, 1);
+          issue_pv(n, 0);
+        } else {
+          issue_pv(n, 0);
+          umma_commit(&empty[n & 1]);
+        }
+      }
+      if (ntiles == 2 && n > 0) { issue_pv(n - 1, 1); umma_commit(&empty[(n - 1) & 1]); }
+    }
+  } else if (warp >= 4) {
+    const int t = (warp - 4) >> 2;        // query tile of this warpgroup
+    const int wq = warp & 3;              // TMEM lane quarter == warp % 4
+    if (t < ntiles) {
+      const int r = wq * 32 + lane;       // row within the tile == TMEM lane
+      const int q = t * 128 + r;
+      const bool warp_has_rows = t * 128 + wq * 32 < p.N;
+      const uint32_t tS = tmem_base + t * 256 + (static_cast<uint32_t>(wq * 32) << 16);
+      const int nch = ncols >> 5;         // full 32-column chunks
+      const bool tail16 = (ncols & 16) != 0;
+      int n = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
+        const int b = u / p.H, hh = u - b * p.H;
+        mbar_wait(&s_full[t], n & 1, 44);
+        tc_fence_after();
+        float l = 0.f, m2 = 0.f;
+        if (warp_has_rows) {
+          // pass 1: row maximum over the valid keys (two register buffers, statically indexed)
+          float mx = -INFINITY;
+          uint32_t va[32], vb[32];
+          auto max_chunk = [&](const uint32_t (&x)[32], int c) {
+            if ((c + 1) * 32 <= p.N) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(x[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, c * 32 + i < p.N ? __uint_as_float(x[i]) : -INFINITY);
+            }
+          };
+          if (nch > 0) tmem_ld32(tS, va);
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nch) tmem_ld32(tS + (c + 1) * 32, vb);
+            max_chunk(va, c);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld32(tS + (c + 2) * 32, va);
+              max_chunk(vb, c + 1);
+            }
+          }
+          if (tail16) {
+            uint32_t w[16];
+            tmem_ld16(tS + nch * 32, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, nch * 32 + i < p.N ? __uint_as_float(w[i]) : -INFINITY);
+          }
+          m2 = mx * p.scale_log2e;
+          // pass 2: probabilities -> packed bf16 written over the S columns already consumed
+          auto exp_chunk = [&](const uint32_t (&x)[32], int c) {
+            uint32_t w[16];
+            if ((c + 1) * 32 <= p.N) {  // warp-uniform: the hot path carries no masking code
+#pragma unroll
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), p.scale_log2e, -m2));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(x[i + 1]), p.scale_log2e, -m2));
+                l += p0 + p1;
+                w[i >> 1] = pack_bf16(p0, p1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), p.scale_log2e, -m2));
+                float p1 = ex2_approx(fmaf(__uint_as_float(x[i + 1]), p.scale_log2e, -m2));
+                if (c * 32 + i >= p.N) p0 = 0.f;
+                if (c * 32 + i + 1 >= p.N) p1 = 0.f;
+                l += p0 + p1;
+                w[i >> 1] = pack_bf16(p0, p1);
+              }
+            }
+            tmem_st16(tS + c * 16, w);
+          };
+          if (nch > 0) tmem_ld32(tS, va);
+          for (int c = 0; c < nch; c += 2) {
+            tmem_ld_wait();
+            if (c + 1 < nch) tmem_ld32(tS + (c + 1) * 32, vb);
+            exp_chunk(va, c);
+            if (c + 1 < nch) {
+              tmem_ld_wait();
+              if (c + 2 < nch) tmem_ld32(tS + (c + 2) * 32, va);
+              exp_chunk(vb, c + 1);
+            }
+          }
+          if (tail16) {
+            uint32_t x[16], w[16];
+            tmem_ld16(tS + nch * 32, x);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), p.scale_log2e, -m2));
+              float p1 = ex2_approx(fmaf(__uint_as_float(x[i + 1]), p.scale_log2e, -m2));
+              if (nch * 32 + i >= p.N) p0 = 0.f;
+              if (nch * 32 + i + 1 >= p.N) p1 = 0.f;
+              l += p0 + p1;
+              w[i >> 1] = pack_bf16(p0, p1);
+            }
+#pragma unroll
+            for (int i = 8; i < 16; ++i) w[i] = 0u;
+            // 8 packed columns; the x16 store also clears 8 columns beyond ncols/2, which nothing reads
+            tmem_st16(tS + nch * 16, w);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[t]);
+        // ---- O = P V is being computed; then normalise and store ----
+        mbar_wait(&o_full[t], n & 1, 45);
+        tc_fence_after();
+        if (warp_has_rows) {
+          uint32_t o0[32], o1[32];
+          tmem_ld32(tS + 128, o0);
+          tmem_ld32(tS + 160, o1);
+          tmem_ld_wait();
+          if (q < p.N) {
+            const float inv = 1.0f / l;
+            __nv_bfloat16* orow = p.o + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 w;
+              w.x = pack_bf16(__uint_as_float(o0[c * 8 + 0]) * inv, __uint_as_float(o0[c * 8 + 1]) * inv);
+              w.y = pack_bf16(__uint_as_float(o0[c * 8 + 2]) * inv, __uint_as_float(o0[c * 8 + 3]) * inv);
+              w.z = pack_bf16(__uint_as_float(o0[c * 8 + 4]) * inv, __uint_as_float(o0[c * 8 + 5]) * inv);
+              w.w = pack_bf16(__uint_as_float(o0[c * 8 + 6]) * inv, __uint_as_float(o0[c * 8 + 7]) * inv);
+              reinterpret_cast<uint4*>(orow)[c] = w;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4 w;
+              w.x = pack_bf16(__uint_as_float(o1[c * 8 + 0]) * inv, __uint_as_float(o1[c * 8 + 1]) * inv);
+              w.y = pack_bf16(__uint_as_float(o1[c * 8 + 2]) * inv, __uint_as_float(o1[c * 8 + 3]) * inv);
+              w.z = pack_bf16(__uint_as_float(o1[c * 8 + 4]) * inv, __uint_as_float(o1[c * 8 + 5]) * inv);
+              w.w = pack_bf16(__uint_as_float(o1[c * 8 + 6]) * inv, __uint_as_float(o1[c * 8 + 7]) * inv);
+              reinterpret_cast<uint4*>(orow)[4 + c] = w;
+            }
+            if (p.lse != nullptr) p.lse[((long long)b * p.H + hh) * p.N + q] = m2 * LN2 + logf(l);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_free[t]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// --------------------------------------------------------------------------------------------------
 // Backward
 // --------------------------------------------------------------------------------------------------
 struct BwdSmem {
@@ -762,6 +1032,15 @@ int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, i
   p.o = (__nv_bfloat16*)o; p.lse = lse;
   dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!causal && N <= 256 && g_debug[7] == 0) {
+    // short sequences: persistent kernel, whole head resident, exact single-shot softmax, P in TMEM
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdShortSmem::TOTAL));
+    const int units = B * H;
+    const int g = units < num_sms() ? units : num_sms();
+    attn_fwd_short_kernel<<<g, AS_THREADS, FwdShortSmem::TOTAL, st>>>(tm, p);
+    B200_CUDA(cudaGetLastError());
+    return OK;
+  }
   if (causal) {
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
     attn_fwd_kernel<true><<<grid, AT_THREADS, FwdSmem::TOTAL, st>>>(tm, p);
@@ -796,7 +1075,7 @@ int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
   p.lse = const_cast<float*>(lse);
   p.o_in = (const __nv_bfloat16*)o; p.do_in = (const __nv_bfloat16*)d_o;
   p.dq_acc = (float*)workspace; p.dqkv = (__nv_bfloat16*)dqkv;
-  if (N <= 256 && g_debug[5] == 0) {
+  if (N <= 256 && g_debug[7] == 0) {
     // short sequences: everything resident per (batch, head), no HBM accumulation
     dim3 grid_small(H, B);
     if (causal) {
