@@ -49,6 +49,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// true in exactly one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // K-major SWIZZLE_128B tile (rows of 128 bytes): descriptor for the 16-element K slice `k16` (0..3)
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k16) {
   return umma_smem_desc(tile_addr + k16 * 32, 16, 1024);
@@ -989,6 +1002,415 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
   if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// --------------------------------------------------------------------------------------------------
+// Backward for short sequences, second generation (N <= 208, no causal mask): persistent, one CTA per SM, a work
+// unit is one (batch, head), everything of the head resident.  The score matrix is computed TRANSPOSED,
+// S^T = K Q^T, so TMEM lanes are KEYS:
+//   * P^T and dS^T (bf16) are written back over the dead S^T / dP^T columns and feed dV = P^T dO and
+//     dK = dS^T Q directly as TMEM A operands (tcgen05.mma, A in TMEM): P never touches shared memory;
+//   * dV_j / dK_j of a 128-key tile come out of ONE accumulation over all queries (no loop-carried accumulators),
+//     into the columns freed by the bf16 rewrite; only dS^T additionally goes to shared memory (as the
+//     MN-major A operand of dQ = dS K, issued once per unit when both key tiles are done);
+//   * two warpgroups split the QUERY columns (tile 0: 128, tile 1: the rest); there are no fp32 atomics, no dQ
+//     workspace and no conversion pass;
+//   * MMAs that accumulate into the same TMEM tile are dependent (~90 clk each at N = 64), so independent
+//     accumulators are interleaved (S / dP, dV / dK, dQ_0 / dQ_1);
+//   * results leave through swizzled shared-memory staging (operand slots that are dead by then) and TMA stores;
+//   * two otherwise idle warps compute the per-query statistics (-lse log2e, D = rowsum(dO o O)) of the NEXT unit
+//     while this one runs (lanes are keys, so the statistics are needed as shared-memory vectors).
+// The softmax scale of dS is applied when dQ / dK are read out (64 values per row instead of N).
+// TMEM: S^T [0,128)+[128,128+w1), dP^T [256,384)+[384,384+w1); P^T over the first half of each S^T part, dS^T over
+// the first half of each dP^T part; dV_j [64,128), dK_j [320,384); dQ_0 [128,192), dQ_1 [192,256).
+// Shared memory (packed rows, ncols = ceil16(N)): K | V | Q | dO ([ncols x 128 B] each) | dS^T slabs (64 queries
+// wide, [ncols keys x 128 B] each, 2 per query tile) | staging tile X | statistic vectors | barriers.
+// --------------------------------------------------------------------------------------------------
+constexpr int AB2_THREADS = 384;  // warp 0: TMA, warp 1: MMA, warps 2-3: statistics (2: TMEM alloc), warps 4-7 / 8-11: query tile 0 / 1
+
+struct Bwd2Layout {
+  int OP;       // bytes of one packed operand / dS^T slab = ncols * 128
+  int sK, sV, sQ, sDO, sDS, sX, vec, bar, total;
+  __host__ __device__ Bwd2Layout(int ncols, int nq) {
+    OP = ncols * 128;
+    sK = 0; sV = OP; sQ = 2 * OP; sDO = 3 * OP; sDS = 4 * OP;
+    sX = sDS + 2 * nq * OP;        // [128 x 128 B] output staging tile (1024-aligned: OP is a multiple of 2048)
+    vec = sX + AT_TILE_BYTES;
+    bar = vec + 2 * 256 * 4;       // (-lse log2e, D) x 256 queries
+    total = bar + 256;
+  }
+  // The M = 128 A-operand tiles (K_j, V_j) always span 128 rows: for tiny sequences they reach past the packed
+  // operands, so the allocation must at least cover them (the surplus rows only feed lanes that are never stored).
+  __host__ __device__ int alloc_bytes(int nq) const {
+    const int need = sV + nq * 16384 + 1024;
+    return total > need ? total : need;
+  }
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One warp: 32 rows x 64 fp32 TMEM columns (scaled) -> bf16 -> swizzled staging rows -> one TMA store (box 64 x 32).
+__device__ __forceinline__ void bwd2_store_tile(uint32_t tsrc, float sc, uint8_t* stage_rows, bool write_ok,
+                                                const CUtensorMap* tm_out, int col, int row, int b, int lane) {
+  if (lane == 0) bulk_wait_read();  // this warp's previous store has finished reading its staging rows
+  __syncwarp();
+  uint32_t v0[32], v1[32];
+  tmem_ld32(tsrc, v0);
+  tmem_ld32(tsrc + 32, v1);
+  tmem_ld_wait();
+  if (write_ok) {
+    uint8_t* rowp = stage_rows + lane * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 w;
+      w.x = pack_bf16(__uint_as_float(v0[c * 8 + 0]) * sc, __uint_as_float(v0[c * 8 + 1]) * sc);
+      w.y = pack_bf16(__uint_as_float(v0[c * 8 + 2]) * sc, __uint_as_float(v0[c * 8 + 3]) * sc);
+      w.z = pack_bf16(__uint_as_float(v0[c * 8 + 4]) * sc, __uint_as_float(v0[c * 8 + 5]) * sc);
+      w.w = pack_bf16(__uint_as_float(v0[c * 8 + 6]) * sc, __uint_as_float(v0[c * 8 + 7]) * sc);
+      *reinterpret_cast<uint4*>(rowp + ((c ^ (lane & 7)) << 4)) = w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 w;
+      w.x = pack_bf16(__uint_as_float(v1[c * 8 + 0]) * sc, __uint_as_float(v1[c * 8 + 1]) * sc);
+      w.y = pack_bf16(__uint_as_float(v1[c * 8 + 2]) * sc, __uint_as_float(v1[c * 8 + 3]) * sc);
+      w.z = pack_bf16(__uint_as_float(v1[c * 8 + 4]) * sc, __uint_as_float(v1[c * 8 + 5]) * sc);
+      w.w = pack_bf16(__uint_as_float(v1[c * 8 + 6]) * sc, __uint_as_float(v1[c * 8 + 7]) * sc);
+      *reinterpret_cast<uint4*>(rowp + (((4 + c) ^ (lane & 7)) << 4)) = w;
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm_out, stage_rows, col, row, b);
+    bulk_commit();
+  }
+}
+
+__global__ void __launch_bounds__(AB2_THREADS, 1)
+attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid_constant__ CUtensorMap tm_qkv_b,
+                      const __grid_constant__ CUtensorMap tm_do_a, const __grid_constant__ CUtensorMap tm_do_b,
+                      const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t at_smem_raw[];
+  uint8_t* smem = at_smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int ncols = ((p.N + 15) >> 4) << 4;
+  const int nt = (p.N + 127) >> 7;               // query tiles == key tiles (1 or 2)
+  const int w0 = ncols < 128 ? ncols : 128, w1 = ncols - w0;
+  const Bwd2Layout L(ncols, nt);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar);
+  uint64_t* full = bars + 0;        // operands of the unit loaded
+  uint64_t* empty = bars + 1;       // operands consumed: dQ MMAs done and every warp's last store read its staging
+  uint64_t* sdp_full = bars + 2;    // [2] S^T, dP^T columns of query tile i complete
+  uint64_t* pds_ready = bars + 4;   // [2] P^T, dS^T of query tile i written (4 warps)
+  uint64_t* dkv_full = bars + 6;    // dV_j, dK_j complete
+  uint64_t* dkv_free = bars + 7;    // dV_j, dK_j read out (4 nt warps)
+  uint64_t* dq_full = bars + 8;     // dQ complete
+  uint64_t* dq_free = bars + 9;     // dQ read out (4 nt warps)
+  uint64_t* stats_full = bars + 10; // statistic vectors of the unit written (2 warps)
+  uint64_t* stats_free = bars + 11; // statistic vectors no longer read (4 nt warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* nlse = reinterpret_cast<float*>(smem + L.vec);
+  float* Dv = nlse + 256;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = p.B * p.H;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_qkv_a); tma_prefetch_desc(&tm_qkv_b);
+    tma_prefetch_desc(&tm_do_a); tma_prefetch_desc(&tm_do_b); tma_prefetch_desc(&tm_out);
+    mbar_init(full, 1); mbar_init(empty, 1 + 4 * nt);
+    mbar_init(&sdp_full[0], 1); mbar_init(&sdp_full[1], 1);
+    mbar_init(&pds_ready[0], 4); mbar_init(&pds_ready[1], 4);
+    mbar_init(dkv_full, 1); mbar_init(dkv_free, 4 * nt);
+    mbar_init(dq_full, 1); mbar_init(dq_free, 4 * nt);
+    mbar_init(stats_full, 2); mbar_init(stats_free, 4 * nt);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
+        const int b = u / p.H, hh = u - b * p.H;
+        mbar_wait(empty, (n & 1) ^ 1, 90);
+        mbar_expect_tx(full, 4 * L.OP);
+        // order: what the first S^T MMA needs (K, Q) first
+        tma_load_3d(smem + L.sK, &tm_qkv_a, full, p.d + hh * AT_HD, 0, b);
+        tma_load_3d(smem + L.sQ, &tm_qkv_a, full, hh * AT_HD, 0, b);
+        if (w1 > 0) tma_load_3d(smem + L.sQ + 16384, &tm_qkv_b, full, hh * AT_HD, 128, b);
+        tma_load_3d(smem + L.sV, &tm_qkv_a, full, 2 * p.d + hh * AT_HD, 0, b);
+        tma_load_3d(smem + L.sDO, &tm_do_a, full, hh * AT_HD, 0, b);
+        if (w1 > 0) {
+          tma_load_3d(smem + L.sDO + 16384, &tm_do_b, full, hh * AT_HD, 128, b);
+          tma_load_3d(smem + L.sK + 16384, &tm_qkv_b, full, p.d + hh * AT_HD, 128, b);
+          tma_load_3d(smem + L.sV + 16384, &tm_qkv_b, full, 2 * p.d + hh * AT_HD, 128, b);
+        }
+        // there is no room for a second operand stage: pull the NEXT unit's tiles into L2 now, so that its loads
+        // (issued when this unit releases the operands) are L2 hits
+        const int u2 = u + gridDim.x;
+        if (u2 < units) {
+          const int b2 = u2 / p.H, h2 = u2 - b2 * p.H;
+          tma_prefetch_3d(&tm_qkv_a, p.d + h2 * AT_HD, 0, b2);
+          tma_prefetch_3d(&tm_qkv_a, h2 * AT_HD, 0, b2);
+          tma_prefetch_3d(&tm_qkv_a, 2 * p.d + h2 * AT_HD, 0, b2);
+          tma_prefetch_3d(&tm_do_a, h2 * AT_HD, 0, b2);
+          if (w1 > 0) {
+            tma_prefetch_3d(&tm_qkv_b, p.d + h2 * AT_HD, 128, b2);
+            tma_prefetch_3d(&tm_qkv_b, h2 * AT_HD, 128, b2);
+            tma_prefetch_3d(&tm_qkv_b, 2 * p.d + h2 * AT_HD, 128, b2);
+            tma_prefetch_3d(&tm_do_b, h2 * AT_HD, 128, b2);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // The whole warp runs the (warp-uniform) control flow and descriptor arithmetic, one elected lane issues:
+    // descriptors then live in uniform registers and an MMA costs a handful of issue slots.  With everything
+    // inside `if (lane == 0)` the address arithmetic is per-thread code and the N = 64 MMAs (32 clk of tensor
+    // work each) were bound by the ~80 clk of scalar instructions between them.
+    const bool elected = elect_one();
+    constexpr uint32_t idesc_ts = umma_idesc_bf16(128, AT_HD, false, true);   // dV, dK: A in TMEM, B MN-major
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, AT_HD, true, true);    // dQ: A = dS^T slabs (MN-major)
+    const uint32_t sK = smem_u32(smem + L.sK), sV = smem_u32(smem + L.sV), sQ = smem_u32(smem + L.sQ),
+                   sDO = smem_u32(smem + L.sDO), sDS = smem_u32(smem + L.sDS);
+    const uint32_t idesc_s0 = umma_idesc_bf16(128, w0, false, false);
+    const uint32_t idesc_s1 = umma_idesc_bf16(128, w1 > 0 ? w1 : 16, false, false);
+    int n = 0, cc = 0;  // unit counter, chain (key tile) counter
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
+      mbar_wait(full, n & 1, 91);
+      for (int j = 0; j < nt; ++j, ++cc) {
+        // TMEM reuse: the previous chain's dV/dK (and, for the unit's first chain, the previous unit's dQ)
+        // must have been read out before S^T / dP^T are overwritten
+        if (cc > 0) mbar_wait(dkv_free, (cc - 1) & 1, 92);
+        if (j == 0 && n > 0) mbar_wait(dq_free, (n - 1) & 1, 93);
+        tc_fence_after();
+        const uint64_t aK = desc_kmajor(sK + j * 16384, 0), aV = desc_kmajor(sV + j * 16384, 0);
+        for (int i = 0; i < nt; ++i) {
+          const uint32_t idesc_s = i == 0 ? idesc_s0 : idesc_s1;
+          const uint64_t bQ = desc_kmajor(sQ + i * 16384, 0), bDO = desc_kmajor(sDO + i * 16384, 0);
+          const uint32_t tS = tmem_base + i * 128, tdP = tmem_base + 256 + i * 128;
+          if (elected) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // S^T and dP^T are independent accumulators: alternate them
+              umma_bf16(tS, aK + 2 * k, bQ + 2 * k, idesc_s, k > 0);      // +32 bytes per 16-element K slice
+              umma_bf16(tdP, aV + 2 * k, bDO + 2 * k, idesc_s, k > 0);
+            }
+            umma_commit(&sdp_full[i]);
+          }
+          __syncwarp();
+        }
+        for (int i = 0; i < nt; ++i) {
+          const int ksteps = (i == 0 ? w0 : w1) >> 4;
+          mbar_wait(&pds_ready[i], cc & 1, 94);
+          tc_fence_after();
+          uint64_t bDO = desc_mnmajor(sDO + i * 16384, 0, 8192), bQ = desc_mnmajor(sQ + i * 16384, 0, 8192);
+          uint32_t aP = tmem_base + i * 128, aDS = tmem_base + 256 + i * 128;
+          uint32_t acc = i > 0 ? 1u : 0u;
+#pragma unroll 2
+          for (int k = 0; k < ksteps; ++k) {
+            if (elected) {
+              umma_bf16_ts(tmem_base + 64, aP, bDO, idesc_ts, acc);
+              umma_bf16_ts(tmem_base + 320, aDS, bQ, idesc_ts, acc);
+            }
+            aP += 8; aDS += 8; bDO += 128; bQ += 128;   // 16 queries: 8 packed TMEM columns, 16 rows x 128 B of B
+            acc = 1u;
+          }
+          __syncwarp();
+        }
+        if (elected) umma_commit(dkv_full);
+        __syncwarp();
+      }
+      // dQ_i = dS_i K over all keys; dS^T of both key tiles is in shared memory (pds_ready waited above)
+      {
+        const int ksteps = ncols >> 4;
+        uint64_t a0 = desc_mnmajor(sDS, 0, L.OP), a1 = desc_mnmajor(sDS + 2 * L.OP, 0, L.OP), bK = desc_mnmajor(sK, 0, 8192);
+        uint32_t acc = 0u;
+#pragma unroll 2
+        for (int k = 0; k < ksteps; ++k) {
+          if (elected) {
+            umma_bf16(tmem_base + 128, a0, bK, idesc_dq, acc);
+            if (nt == 2) umma_bf16(tmem_base + 192, a1, bK, idesc_dq, acc);
+          }
+          a0 += 128; a1 += 128; bK += 128;
+          acc = 1u;
+        }
+        if (elected) { umma_commit(dq_full); umma_commit(empty); }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 4) {
+    // ---- statistics of the NEXT unit, computed while the current one runs: thread t owns queries t, t + 64, ... ----
+    const int t = (warp - 2) * 32 + lane;
+    int n = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
+      const int b = u / p.H, hh = u - b * p.H;
+      float a[4], dsum[4];
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int q = t + 64 * s4;
+        a[s4] = -INFINITY; dsum[s4] = 0.f;
+        if (q < p.N) {
+          a[s4] = -__ldg(p.lse + ((long long)b * p.H + hh) * p.N + q) * LOG2E;
+          const uint4* orow = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD);
+          const uint4* drow = reinterpret_cast<const uint4*>(p.do_in + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD);
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 x = __ldg(orow + c), g = __ldg(drow + c);
+            const float2 x0 = unpack_bf16(x.x), x1 = unpack_bf16(x.y), x2 = unpack_bf16(x.z), x3 = unpack_bf16(x.w);
+            const float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
+            acc += x0.x * g0.x + x0.y * g0.y + x1.x * g1.x + x1.y * g1.y + x2.x * g2.x + x2.y * g2.y + x3.x * g3.x + x3.y * g3.y;
+          }
+          dsum[s4] = acc;
+        }
+      }
+      mbar_wait(stats_free, (n & 1) ^ 1, 98);   // the previous unit no longer reads the vectors
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) { nlse[t + 64 * s4] = a[s4]; Dv[t + 64 * s4] = dsum[s4]; }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stats_full);
+    }
+  } else {
+    const int i = (warp - 4) >> 2;     // query tile (column range) of this warpgroup
+    const int wq = warp & 3;           // TMEM lane quarter
+    if (i < nt) {
+      const int r = wq * 32 + lane;    // key row within the key tile == TMEM lane; query row for the dQ read-out
+      const int wi = i == 0 ? w0 : w1;
+      const int nch = wi >> 5;
+      const bool tail16 = (wi & 16) != 0;
+      const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+      const uint32_t tS = tmem_base + i * 128 + lane_off, tdP = tmem_base + 256 + i * 128 + lane_off;
+      int n = 0, cc = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
+        const int b = u / p.H, hh = u - b * p.H;
+        mbar_wait(stats_full, n & 1, 99);
+        for (int j = 0; j < nt; ++j, ++cc) {
+          const int key_local = j * 128 + r;            // row in the packed operands / dS^T slabs
+          const bool warp_has_keys = j * 128 + wq * 32 < ncols;
+          mbar_wait(&sdp_full[i], cc & 1, 95);
+          tc_fence_after();
+          if (warp_has_keys) {
+            const bool store_ok = key_local < ncols;    // rows beyond the padded keys do not exist in the slabs
+            auto do_chunk = [&](const uint32_t (&sv)[32], const uint32_t (&dv)[32], int c, int ncol) {
+              // ncol = 32 or 16 valid S columns in this chunk
+              uint32_t wp[16], wd[16];
+              const float4* lv = reinterpret_cast<const float4*>(nlse + i * 128 + c * 32);
+              const float4* dvv = reinterpret_cast<const float4*>(Dv + i * 128 + c * 32);
+#pragma unroll
+              for (int e4 = 0; e4 < 8; ++e4) {
+                if (e4 * 4 < ncol) {
+                  const float4 a = lv[e4], dd = dvv[e4];
+                  const float p0 = ex2_approx(fmaf(__uint_as_float(sv[e4 * 4 + 0]), p.scale_log2e, a.x));
+                  const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e4 * 4 + 1]), p.scale_log2e, a.y));
+                  const float p2 = ex2_approx(fmaf(__uint_as_float(sv[e4 * 4 + 2]), p.scale_log2e, a.z));
+                  const float p3 = ex2_approx(fmaf(__uint_as_float(sv[e4 * 4 + 3]), p.scale_log2e, a.w));
+                  wp[e4 * 2 + 0] = pack_bf16(p0, p1);
+                  wp[e4 * 2 + 1] = pack_bf16(p2, p3);
+                  wd[e4 * 2 + 0] = pack_bf16(p0 * (__uint_as_float(dv[e4 * 4 + 0]) - dd.x), p1 * (__uint_as_float(dv[e4 * 4 + 1]) - dd.y));
+                  wd[e4 * 2 + 1] = pack_bf16(p2 * (__uint_as_float(dv[e4 * 4 + 2]) - dd.z), p3 * (__uint_as_float(dv[e4 * 4 + 3]) - dd.w));
+                } else {
+                  wp[e4 * 2 + 0] = 0u; wp[e4 * 2 + 1] = 0u; wd[e4 * 2 + 0] = 0u; wd[e4 * 2 + 1] = 0u;
+                }
+              }
+              tmem_st16(tS + c * 16, wp);    // over S^T columns already consumed (16 c <= 32 c)
+              tmem_st16(tdP + c * 16, wd);
+              if (store_ok) {
+                uint8_t* row = smem + L.sDS + (2 * i + (c >> 1)) * L.OP + key_local * 128;
+                const int chunk0 = (c & 1) * 4;
+                const int nq4 = ncol >> 3;   // 16-byte pieces holding valid columns
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  if (q4 < nq4) {
+                    const int chunk = (chunk0 + q4) ^ (key_local & 7);
+                    *reinterpret_cast<uint4*>(row + chunk * 16) = make_uint4(wd[q4 * 4 + 0], wd[q4 * 4 + 1], wd[q4 * 4 + 2], wd[q4 * 4 + 3]);
+                  }
+                }
+              }
+            };
+            uint32_t sv[32], dv[32];
+            for (int c = 0; c < nch; ++c) {
+              tmem_ld32(tS + c * 32, sv);
+              tmem_ld32(tdP + c * 32, dv);
+              tmem_ld_wait();
+              do_chunk(sv, dv, c, 32);
+            }
+            if (tail16) {
+              uint32_t s16[16], d16[16];
+              tmem_ld16(tS + nch * 32, s16);
+              tmem_ld16(tdP + nch * 32, d16);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) { sv[e] = s16[e]; dv[e] = d16[e]; }
+#pragma unroll
+              for (int e = 16; e < 32; ++e) { sv[e] = 0u; dv[e] = 0u; }
+              do_chunk(sv, dv, nch, 16);
+            }
+            tmem_st_wait();
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&pds_ready[i]);
+            if (j == nt - 1) mbar_arrive(stats_free);   // last read of this unit's statistic vectors
+          }
+          // ---- dV_j (warpgroup 0) / dK_j (warpgroup 1, or 0 when there is a single query tile) ----
+          mbar_wait(dkv_full, cc & 1, 96);
+          tc_fence_after();
+          if (warp_has_keys) {
+            const bool wr = key_local < ncols;
+            const int row0 = j * 128 + wq * 32;
+            if (nt == 1 || i == 0)   // dV_j -> staged in the (dead) V_j rows
+              bwd2_store_tile(tmem_base + 64 + lane_off, 1.0f, smem + L.sV + row0 * 128, wr, &tm_out,
+                              2 * p.d + hh * AT_HD, row0, b, lane);
+            if (nt == 1 || i == 1)   // dK_j -> staging tile X
+              bwd2_store_tile(tmem_base + 320 + lane_off, p.scale, smem + L.sX + wq * 4096, wr, &tm_out,
+                              p.d + hh * AT_HD, row0, b, lane);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dkv_free);
+        }
+        // ---- dQ of query tile i: lanes are query rows now; staged in V rows (tile 0) / dO rows (tile 1), both dead ----
+        mbar_wait(dq_full, n & 1, 97);
+        tc_fence_after();
+        if (i * 128 + wq * 32 < ncols)
+          bwd2_store_tile(tmem_base + 128 + 64 * i + lane_off, p.scale, smem + (i == 0 ? L.sV : L.sDO) + wq * 4096,
+                          i * 128 + r < ncols, &tm_out, hh * AT_HD, i * 128 + wq * 32, b, lane);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(dq_free);
+          bulk_wait_read();        // the staging rows inside the operand slots may now be overwritten by TMA loads
+          mbar_arrive(empty);
+        }
+      }
+      if (lane == 0) bulk_wait_all();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // dq_acc fp32 [rows, d] -> bf16 into dqkv[:, 0:d] (row pitch 3d)
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
                                        long long rows, int d) {
@@ -1003,11 +1425,12 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloa
   }
 }
 
-static int make_tmap_bnd(CUtensorMap* tm, const void* base, int B, int N, int row_elems, int seq_first) {
+static int make_tmap_bnd(CUtensorMap* tm, const void* base, int B, int N, int row_elems, int seq_first,
+                         int box_rows = 128) {
   const uint64_t dims[3] = {(uint64_t)row_elems, (uint64_t)N, (uint64_t)B};
   const uint64_t sn = seq_first ? (uint64_t)B : 1, sb = seq_first ? 1 : (uint64_t)N;
   const uint64_t strides[3] = {2, sn * row_elems * 2, sb * row_elems * 2};
-  const uint32_t box[3] = {64, 128, 1};
+  const uint32_t box[3] = {64, (uint32_t)box_rows, 1};
   return make_tmap_nd_bf16(tm, base, 3, dims, strides, box, true);
 }
 
@@ -1075,7 +1498,34 @@ int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
   p.lse = const_cast<float*>(lse);
   p.o_in = (const __nv_bfloat16*)o; p.do_in = (const __nv_bfloat16*)d_o;
   p.dq_acc = (float*)workspace; p.dqkv = (__nv_bfloat16*)dqkv;
-  if (N <= 256 && g_debug[7] == 0) {
+  if (!causal && N <= 208 && g_debug[7] == 0) {
+    // short sequences, transposed formulation: persistent, whole head resident, P^T kept in TMEM
+    const int ncols = ((N + 15) / 16) * 16, nt = (N + 127) / 128;
+    const int w0 = ncols < 128 ? ncols : 128, w1 = ncols - w0;
+    CUtensorMap qa, qb, da, db;
+    rc = make_tmap_bnd(&qa, qkv, B, N, 3 * d, seq_first, w0);
+    if (rc != OK) return rc;
+    rc = make_tmap_bnd(&da, d_o, B, N, d, seq_first, w0);
+    if (rc != OK) return rc;
+    qb = qa; db = da;
+    if (w1 > 0) {
+      rc = make_tmap_bnd(&qb, qkv, B, N, 3 * d, seq_first, w1);
+      if (rc != OK) return rc;
+      rc = make_tmap_bnd(&db, d_o, B, N, d, seq_first, w1);
+      if (rc != OK) return rc;
+    }
+    CUtensorMap tout;
+    rc = make_tmap_bnd(&tout, dqkv, B, N, 3 * d, seq_first, 32);
+    if (rc != OK) return rc;
+    const Bwd2Layout L(ncols, nt);
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.alloc_bytes(nt)));
+    const int units = B * H;
+    const int g = units < num_sms() ? units : num_sms();
+    attn_bwd_short_kernel<<<g, AB2_THREADS, L.alloc_bytes(nt), st>>>(qa, qb, da, db, tout, p);
+    B200_CUDA(cudaGetLastError());
+    return OK;
+  }
+  if (N <= 256 && g_debug[7] != 2) {
     // short sequences: everything resident per (batch, head), no HBM accumulation
     dim3 grid_small(H, B);
     if (causal) {
