@@ -316,18 +316,74 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
 // TMEM columns of tile t (base 256 t): S fp32 [0, ncols), P bf16 [0, ncols/2) (overwrites S behind the reads),
 // O fp32 [128, 192) (S is dead by then).
 // --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One warp: 32 rows x 64 fp32 TMEM columns (scaled per row) -> bf16 -> swizzled staging rows -> one TMA store
+// (box 64 x 32; rows beyond the sequence are clipped by the tensor map).
+__device__ __forceinline__ void bwd2_store_tile(uint32_t tsrc, float sc, uint8_t* stage_rows, bool write_ok,
+                                                const CUtensorMap* tm_out, int col, int row, int b, int lane) {
+  if (lane == 0) bulk_wait_read();  // this warp's previous store has finished reading its staging rows
+  __syncwarp();
+  uint32_t v0[32], v1[32];
+  tmem_ld32(tsrc, v0);
+  tmem_ld32(tsrc + 32, v1);
+  tmem_ld_wait();
+  if (write_ok) {
+    uint8_t* rowp = stage_rows + lane * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 w;
+      w.x = pack_bf16(__uint_as_float(v0[c * 8 + 0]) * sc, __uint_as_float(v0[c * 8 + 1]) * sc);
+      w.y = pack_bf16(__uint_as_float(v0[c * 8 + 2]) * sc, __uint_as_float(v0[c * 8 + 3]) * sc);
+      w.z = pack_bf16(__uint_as_float(v0[c * 8 + 4]) * sc, __uint_as_float(v0[c * 8 + 5]) * sc);
+      w.w = pack_bf16(__uint_as_float(v0[c * 8 + 6]) * sc, __uint_as_float(v0[c * 8 + 7]) * sc);
+      *reinterpret_cast<uint4*>(rowp + ((c ^ (lane & 7)) << 4)) = w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 w;
+      w.x = pack_bf16(__uint_as_float(v1[c * 8 + 0]) * sc, __uint_as_float(v1[c * 8 + 1]) * sc);
+      w.y = pack_bf16(__uint_as_float(v1[c * 8 + 2]) * sc, __uint_as_float(v1[c * 8 + 3]) * sc);
+      w.z = pack_bf16(__uint_as_float(v1[c * 8 + 4]) * sc, __uint_as_float(v1[c * 8 + 5]) * sc);
+      w.w = pack_bf16(__uint_as_float(v1[c * 8 + 6]) * sc, __uint_as_float(v1[c * 8 + 7]) * sc);
+      *reinterpret_cast<uint4*>(rowp + (((4 + c) ^ (lane & 7)) << 4)) = w;
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm_out, stage_rows, col, row, b);
+    bulk_commit();
+  }
+}
+
 constexpr int AS_THREADS = 384;  // warp 0: TMA, warp 1: MMA issue, warp 2: TMEM alloc, warps 4-7 / 8-11: softmax of query tile 0 / 1
 struct FwdShortSmem {
   static constexpr int STAGE = 6 * AT_TILE_BYTES;          // Q0 Q1 | K (256 rows) | V (256 rows) = 96 KB
   static constexpr int Q = 0, K = 2 * AT_TILE_BYTES, V = 4 * AT_TILE_BYTES;
-  static constexpr int BAR = 2 * STAGE;
+  static constexpr int OST = 2 * STAGE;                    // O staging: one [128 x 128 B] tile per query tile
+  static constexpr int BAR = OST + 2 * AT_TILE_BYTES;
   static constexpr int TOTAL = BAR + 256;
 };
 
 __device__ __forceinline__ void tmem_st16_packed(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st16(taddr, v); }
 
 __global__ void __launch_bounds__(AS_THREADS, 1)
-attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
+attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
+                      const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t at_smem_raw[];
   uint8_t* smem = at_smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -380,45 +436,63 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPara
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, ncols, false, false);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, AT_HD, false, true);
-      const int ksteps = ncols >> 4;
-      // Issue order in steady state: S0(n), PV1(n-1), S1(n), PV0(n).  The two warpgroups then run half a period
-      // apart, so one tile's softmax (MUFU-bound) overlaps the other tile's PV MMA, O read-out and hand-offs.
-      // (One issuing thread per tile was measured slower: the warpgroups fall into lock-step and share the MUFU.)
-      auto issue_s = [&](int n, int t) {
-        const uint32_t sbase = smem_u32(smem + (n & 1) * FwdShortSmem::STAGE);
-        const uint32_t sQ = sbase + FwdShortSmem::Q + t * AT_TILE_BYTES, sK = sbase + FwdShortSmem::K;
-        mbar_wait(&o_free[t], (n & 1) ^ 1, 42);  // previous unit's O (same TMEM columns) has been read
-        tc_fence_after();
+    // whole warp runs the control flow (descriptor arithmetic stays in uniform registers), one elected lane issues
+    const bool elected = elect_one();
+    const uint32_t idesc_s = umma_idesc_bf16(128, ncols, false, false);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, AT_HD, false, true);
+    const int ksteps = ncols >> 4;
+    // Issue order in steady state: S0(n), PV1(n-1), S1(n), PV0(n).  The two warpgroups then run half a period
+    // apart, so one tile's softmax (MUFU-bound) overlaps the other tile's PV MMA, O read-out and hand-offs.
+    // (One issuing thread per tile was measured slower: the warpgroups fall into lock-step and share the MUFU.)
+    auto issue_s = [&](int n, int t) {
+      const uint32_t sbase = smem_u32(smem + (n & 1) * FwdShortSmem::STAGE);
+      const uint64_t dQ = desc_kmajor(sbase + FwdShortSmem::Q + t * AT_TILE_BYTES, 0);
+      const uint64_t dK = desc_kmajor(sbase + FwdShortSmem::K, 0);
+      mbar_wait(&o_free[t], (n & 1) ^ 1, 42);  // previous unit's O (same TMEM columns) has been read
+      tc_fence_after();
+      if (elected) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tmem_base + t * 256, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + t * 256, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0);
         umma_commit(&s_full[t]);
-      };
-      auto issue_pv = [&](int n, int t) {
-        const uint32_t sV = smem_u32(smem + (n & 1) * FwdShortSmem::STAGE) + FwdShortSmem::V;
-        mbar_wait(&p_ready[t], n & 1, 43);
-        tc_fence_after();
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16_ts(tmem_base + t * 256 + 128, tmem_base + t * 256 + k * 8, desc_mnmajor(sV, k, 8192), idesc_o, k > 0);
-        umma_commit(&o_full[t]);
-      };
-      int n = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
-        mbar_wait(&full[n & 1], (n >> 1) & 1, 41);
-        issue_s(n, 0);
-        if (ntiles == 2) {
-          if (n > 0) { issue_pv(n - 1, 1); umma_commit(&empty[(n - 1) & 1]); }  // stage n-1 fully consumed
-          issue_s(n, 1);
-          issue_pv(n, 0);
-        } else {
-          issue_pv(n, 0);
-          umma_commit(&empty[n & 1]);
-        }
       }
-      if (ntiles == 2 && n > 0) { issue_pv(n - 1, 1); umma_commit(&empty[(n - 1) & 1]); }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int n, int t) {
+      uint64_t dV = desc_mnmajor(smem_u32(smem + (n & 1) * FwdShortSmem::STAGE) + FwdShortSmem::V, 0, 8192);
+      uint32_t aP = tmem_base + t * 256;
+      mbar_wait(&p_ready[t], n & 1, 43);
+      tc_fence_after();
+      uint32_t acc = 0u;
+#pragma unroll 2
+      for (int k = 0; k < ksteps; ++k) {
+        if (elected) umma_bf16_ts(tmem_base + t * 256 + 128, aP, dV, idesc_o, acc);
+        aP += 8; dV += 128; acc = 1u;     // 16 keys: 8 packed TMEM columns of P, 16 rows x 128 B of V
+      }
+      if (elected) umma_commit(&o_full[t]);
+      __syncwarp();
+    };
+    int n = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
+      mbar_wait(&full[n & 1], (n >> 1) & 1, 41);
+      issue_s(n, 0);
+      if (ntiles == 2) {
+        if (n > 0) {
+          issue_pv(n - 1, 1);
+          if (elected) umma_commit(&empty[(n - 1) & 1]);  // stage n-1 fully consumed
+          __syncwarp();
+        }
+        issue_s(n, 1);
+        issue_pv(n, 0);
+      } else {
+        issue_pv(n, 0);
+        if (elected) umma_commit(&empty[n & 1]);
+        __syncwarp();
+      }
+    }
+    if (ntiles == 2 && n > 0) {
+      issue_pv(n - 1, 1);
+      if (elected) umma_commit(&empty[(n - 1) & 1]);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int t = (warp - 4) >> 2;        // query tile of this warpgroup
@@ -531,38 +605,16 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPara
         mbar_wait(&o_full[t], n & 1, 45);
         tc_fence_after();
         if (warp_has_rows) {
-          uint32_t o0[32], o1[32];
-          tmem_ld32(tS + 128, o0);
-          tmem_ld32(tS + 160, o1);
-          tmem_ld_wait();
-          if (q < p.N) {
-            const float inv = 1.0f / l;
-            __nv_bfloat16* orow = p.o + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 w;
-              w.x = pack_bf16(__uint_as_float(o0[c * 8 + 0]) * inv, __uint_as_float(o0[c * 8 + 1]) * inv);
-              w.y = pack_bf16(__uint_as_float(o0[c * 8 + 2]) * inv, __uint_as_float(o0[c * 8 + 3]) * inv);
-              w.z = pack_bf16(__uint_as_float(o0[c * 8 + 4]) * inv, __uint_as_float(o0[c * 8 + 5]) * inv);
-              w.w = pack_bf16(__uint_as_float(o0[c * 8 + 6]) * inv, __uint_as_float(o0[c * 8 + 7]) * inv);
-              reinterpret_cast<uint4*>(orow)[c] = w;
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 w;
-              w.x = pack_bf16(__uint_as_float(o1[c * 8 + 0]) * inv, __uint_as_float(o1[c * 8 + 1]) * inv);
-              w.y = pack_bf16(__uint_as_float(o1[c * 8 + 2]) * inv, __uint_as_float(o1[c * 8 + 3]) * inv);
-              w.z = pack_bf16(__uint_as_float(o1[c * 8 + 4]) * inv, __uint_as_float(o1[c * 8 + 5]) * inv);
-              w.w = pack_bf16(__uint_as_float(o1[c * 8 + 6]) * inv, __uint_as_float(o1[c * 8 + 7]) * inv);
-              reinterpret_cast<uint4*>(orow)[4 + c] = w;
-            }
-            if (p.lse != nullptr) p.lse[((long long)b * p.H + hh) * p.N + q] = m2 * LN2 + logf(l);
-          }
+          // normalise, stage as bf16 (swizzled) and leave through one TMA store per warp
+          bwd2_store_tile(tS + 128, 1.0f / l, smem + FwdShortSmem::OST + t * AT_TILE_BYTES + wq * 4096, true, &tm_o,
+                          hh * AT_HD, t * 128 + wq * 32, b, lane);
+          if (q < p.N && p.lse != nullptr) p.lse[((long long)b * p.H + hh) * p.N + q] = m2 * LN2 + logf(l);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&o_free[t]);
       }
+      if (lane == 0) bulk_wait_all();
     }
   }
 
@@ -1045,59 +1097,6 @@ struct Bwd2Layout {
   }
 };
 
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// One warp: 32 rows x 64 fp32 TMEM columns (scaled) -> bf16 -> swizzled staging rows -> one TMA store (box 64 x 32).
-__device__ __forceinline__ void bwd2_store_tile(uint32_t tsrc, float sc, uint8_t* stage_rows, bool write_ok,
-                                                const CUtensorMap* tm_out, int col, int row, int b, int lane) {
-  if (lane == 0) bulk_wait_read();  // this warp's previous store has finished reading its staging rows
-  __syncwarp();
-  uint32_t v0[32], v1[32];
-  tmem_ld32(tsrc, v0);
-  tmem_ld32(tsrc + 32, v1);
-  tmem_ld_wait();
-  if (write_ok) {
-    uint8_t* rowp = stage_rows + lane * 128;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 w;
-      w.x = pack_bf16(__uint_as_float(v0[c * 8 + 0]) * sc, __uint_as_float(v0[c * 8 + 1]) * sc);
-      w.y = pack_bf16(__uint_as_float(v0[c * 8 + 2]) * sc, __uint_as_float(v0[c * 8 + 3]) * sc);
-      w.z = pack_bf16(__uint_as_float(v0[c * 8 + 4]) * sc, __uint_as_float(v0[c * 8 + 5]) * sc);
-      w.w = pack_bf16(__uint_as_float(v0[c * 8 + 6]) * sc, __uint_as_float(v0[c * 8 + 7]) * sc);
-      *reinterpret_cast<uint4*>(rowp + ((c ^ (lane & 7)) << 4)) = w;
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 w;
-      w.x = pack_bf16(__uint_as_float(v1[c * 8 + 0]) * sc, __uint_as_float(v1[c * 8 + 1]) * sc);
-      w.y = pack_bf16(__uint_as_float(v1[c * 8 + 2]) * sc, __uint_as_float(v1[c * 8 + 3]) * sc);
-      w.z = pack_bf16(__uint_as_float(v1[c * 8 + 4]) * sc, __uint_as_float(v1[c * 8 + 5]) * sc);
-      w.w = pack_bf16(__uint_as_float(v1[c * 8 + 6]) * sc, __uint_as_float(v1[c * 8 + 7]) * sc);
-      *reinterpret_cast<uint4*>(rowp + (((4 + c) ^ (lane & 7)) << 4)) = w;
-    }
-  }
-  fence_proxy_async_smem();
-  __syncwarp();
-  if (lane == 0) {
-    tma_store_3d(tm_out, stage_rows, col, row, b);
-    bulk_commit();
-  }
-}
-
 __global__ void __launch_bounds__(AB2_THREADS, 1)
 attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid_constant__ CUtensorMap tm_qkv_b,
                       const __grid_constant__ CUtensorMap tm_do_a, const __grid_constant__ CUtensorMap tm_do_b,
@@ -1458,9 +1457,12 @@ int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, i
   if (!causal && N <= 256 && g_debug[7] == 0) {
     // short sequences: persistent kernel, whole head resident, exact single-shot softmax, P in TMEM
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdShortSmem::TOTAL));
+    CUtensorMap tm_o;
+    rc = make_tmap_bnd(&tm_o, o, B, N, d, seq_first, 32);
+    if (rc != OK) return rc;
     const int units = B * H;
     const int g = units < num_sms() ? units : num_sms();
-    attn_fwd_short_kernel<<<g, AS_THREADS, FwdShortSmem::TOTAL, st>>>(tm, p);
+    attn_fwd_short_kernel<<<g, AS_THREADS, FwdShortSmem::TOTAL, st>>>(tm, tm_o, p);
     B200_CUDA(cudaGetLastError());
     return OK;
   }
