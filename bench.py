@@ -37,6 +37,16 @@ def train_flops_per_image():
     return 3 * (LAYERS * f_layer + f_head) + 2 * f_patch
 
 
+def load_gemm_traffic():
+    """Per-launch DRAM bytes (read + write) of the tcgen05 GEMM family from the committed `ncu --set full` capture
+    (profiles/r1_gemm_traffic.json, written by tools/ncu_step_summary.py); None when no capture is committed."""
+    path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    try:
+        return float(json.load(open(path))["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -61,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -93,7 +103,18 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            # the timed region was shorter than one sampling period: fall back to a single query taken right
+            # after it (the GPU is still warm; this under-reports the load clocks and is marked as such)
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=10).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                rs = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                        f[5:9]) if v.lower().startswith("active")]
+                return {"sm_mhz": float(f[1]), "sm_max_mhz": float(f[2]), "reasons": rs, "samples": 0,
+                        "note": "single query right after the timed region"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -294,7 +315,8 @@ def run_gpu_arm(args):
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all Linear fwd/dgrad/wgrad launches of a step)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
-                     "traffic": None, "launches_timed": gemm_calls,
+                     "traffic": load_gemm_traffic(), "traffic_unit": "bytes/launch (dram read+write, ncu)",
+                     "flops_per_launch": gemm_flops / gemm_calls if gemm_calls else None, "launches_timed": gemm_calls,
                      "step_tflops_per_gpu": step_tflops, "step_frac_of_peak": step_tflops / peak if peak else None,
                      "step_frac_of_nominal_2250": step_tflops / 2250.0},
         "final_loss": losses[-1] if losses else None,
