@@ -42,6 +42,10 @@ int b200vit_gemm_bias_gelu(const void* x, const void* w, const float* bias, void
 /* out[M,N](f32) = resid[M,N](f32) + x w^T + bias       transformer.py:39,44 ; blocks.py:53,67,69     */
 int b200vit_gemm_bias_residual(const void* x, const void* w, const float* bias, const float* resid,
                                float* out, int M, int N, int K, void* stream);
+/* out[M,N](f32) = resid + dropout_p(x w^T + bias)      mlp[2] + nn.Dropout + residual, transformer.py:39-40,44;
+ * keep mask = function of (seed, row, column) (csrc/dropout.cuh), kept values scaled by 1 / (1 - p)          */
+int b200vit_gemm_bias_dropout_residual(const void* x, const void* w, const float* bias, const float* resid,
+                                       float* out, int M, int N, int K, float p, unsigned int seed, void* stream);
 /* out[M,N](f32) = x w^T + bias                                                                        */
 int b200vit_gemm_bias_f32(const void* x, const void* w, const float* bias, float* out, int M, int N,
                           int K, void* stream);
@@ -63,7 +67,7 @@ int b200vit_gemm_wgrad_bias(const void* dy, const void* x, float* dw, float* db,
  * qkv: [B, N, 3, H, 64] bf16 == the row-major output of the QKV Linear, "(qkv h d)" of transformer.py:27;
  * o: [B, N, H*64] bf16 == "b h n d -> b n (h d)" of transformer.py:29; lse: [B, H, N] fp32 (may be NULL).
  * Replaces F.scaled_dot_product_attention at transformer.py:28 (causal = additive -inf mask of
- * transformer.py:22-25) and the SDPA inside nn.MultiheadAttention (blocks.py:60).  dropout_p must be 0.
+ * transformer.py:22-25) and the SDPA inside nn.MultiheadAttention (blocks.py:60).
  * seq_first != 0: tensors are [N, B, ...] (the LND layout of blocks.py:270) instead of [B, N, ...]. */
 int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int causal, int seq_first,
                            void* stream);
@@ -72,6 +76,14 @@ size_t b200vit_flash_attn_bwd_workspace_size(int B, int N, int H);
 int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B,
                            int N, int H, int causal, int seq_first, void* workspace, size_t workspace_bytes,
                            void* stream);
+/* The same with dropout on the attention probabilities (dropout_p of F.scaled_dot_product_attention,
+ * transformer.py:28 -- applied in eval mode too, as the reference does).  The keep mask is a pure function of
+ * (seed, batch*H + head, query, key) (csrc/dropout.cuh): backward regenerates it from the same seed.        */
+int b200vit_flash_attn_fwd_dropout(const void* qkv, void* o, float* lse, int B, int N, int H, int causal,
+                                   int seq_first, float dropout_p, unsigned int seed, void* stream);
+int b200vit_flash_attn_bwd_dropout(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
+                                   int B, int N, int H, int causal, int seq_first, float dropout_p,
+                                   unsigned int seed, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- LayerNorm on the fp32 residual stream (F.layer_norm transformer.py:43-44; nn.LayerNorm blocks.py:43,48)
  * fwd: v = x (+ add_bf16) ; x_out = v (optional) ; y = LN(v) * gamma + beta -> bf16 and/or fp32 ; saves mean, rstd
@@ -85,6 +97,13 @@ int b200vit_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float*
 int b200vit_colsum_bf16(const void* a, float* out, int M, int N, int accumulate, void* stream);
 int b200vit_colsum_f32(const float* a, float* out, int rows, int n, void* stream);
 int b200vit_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+/* out(bf16) = x(f32) * keep / (1 - p): backward of nn.Dropout (transformer.py:40) fused with the cast that feeds the
+ * fc2 dgrad / wgrad GEMMs; same mask function as b200vit_gemm_bias_dropout_residual                          */
+int b200vit_dropout_cast_bf16(const float* x, void* out_bf16, long long M, int d, float p, unsigned int seed,
+                              void* stream);
+/* test aids: the keep masks as bytes, [M, d] and [B, H, N, N]                                                */
+int b200vit_dropout_mask_rows(unsigned char* out, long long M, int d, float p, unsigned int seed, void* stream);
+int b200vit_dropout_mask_attn(unsigned char* out, int B, int H, int N, float p, unsigned int seed, void* stream);
 
 /* ---- patch embedding (train_vit.py:34-45, blocks.py:235-237,257-267) ------------------------------------
  * tokens[B, extra+P, d](f32): rows [0,extra) = extra_emb, rows [extra, ..) = conv(x) + bias + pos_emb.

@@ -90,7 +90,9 @@ def gelu_bwd(dg, u):
 # F.scaled_dot_product_attention(q,k,v, attn_mask=-inf upper triangle or None) (transformer.py:22-28)
 # q,k,v: [B,h,N,hd]; scale 1/sqrt(hd); dropout_p = 0 (parity is only defined at p = 0)
 # ------------------------------------------------------------------------------------------------
-def sdpa_fwd(q, k, v, causal=False):
+def sdpa_fwd(q, k, v, causal=False, keep=None, dropout_p=0.0):
+    """F.scaled_dot_product_attention (transformer.py:28).  `keep` (bool [.., n, n]) with `dropout_p` restates its
+    dropout: the softmax probabilities are multiplied by keep / (1 - p) before they weight v."""
     hd = q.shape[-1]
     s = (q @ np.swapaxes(k, -1, -2)) * q.dtype.type(1.0 / math.sqrt(hd))
     if causal:
@@ -100,15 +102,19 @@ def sdpa_fwd(q, k, v, causal=False):
     m = s.max(axis=-1, keepdims=True)
     e = np.exp(s - m)
     p = e / e.sum(axis=-1, keepdims=True)
-    o = p @ v
-    return o.astype(q.dtype), (q, k, v, p.astype(q.dtype))
+    pd = p if keep is None else p * keep * q.dtype.type(1.0 / (1.0 - dropout_p))
+    o = pd @ v
+    return o.astype(q.dtype), (q, k, v, p.astype(q.dtype), keep, dropout_p)
 
 
 def sdpa_bwd(do, cache):
-    q, k, v, p = cache
+    q, k, v, p, keep, dropout_p = cache
     hd = q.shape[-1]
-    dv = np.swapaxes(p, -1, -2) @ do
-    dp = do @ np.swapaxes(v, -1, -2)
+    r = q.dtype.type(1.0 if keep is None else 1.0 / (1.0 - dropout_p))
+    pd = p if keep is None else p * keep * r
+    dv = np.swapaxes(pd, -1, -2) @ do
+    dpd = do @ np.swapaxes(v, -1, -2)
+    dp = dpd if keep is None else dpd * keep * r
     ds = p * (dp - (dp * p).sum(axis=-1, keepdims=True))
     ds = ds * q.dtype.type(1.0 / math.sqrt(hd))
     dq = ds @ k

@@ -53,8 +53,11 @@ def test_unsupported_configs_fail_loudly():
     from b200vit import modules as M
     with pytest.raises(NotImplementedError):
         M.Transformer(M.TransformerConfig(n_layers=1, n_heads=4, n_embd=128, block_size=8))  # head_dim 32
-    with pytest.raises(NotImplementedError):
-        M.Transformer(M.TransformerConfig(n_layers=1, n_heads=2, n_embd=128, block_size=8, dropout=0.1))
+    with pytest.raises(ValueError):
+        M.Transformer(M.TransformerConfig(n_layers=1, n_heads=2, n_embd=128, block_size=8, dropout=1.0))
+    md = M.Transformer(M.TransformerConfig(n_layers=1, n_heads=2, n_embd=128, block_size=8, dropout=0.15))
+    assert M._dropout_pair(md.layers[0]) == (0.15, 0.15)          # training: attention + MLP dropout
+    assert M._dropout_pair(md.layers[0].eval()) == (0.15, 0.0)    # eval: SDPA dropout stays on (transformer.py:28)
     m = M.Transformer(M.TransformerConfig(n_layers=1, n_heads=2, n_embd=128, block_size=8))
     with pytest.raises(Exception):
         m(torch.zeros(1, 8, 128))  # CPU tensors: no fallback

@@ -197,6 +197,57 @@ def test_flash_attention(ops, B, N, H, causal):
     _attn_case(ops, B, N, H, causal, seed=N + H)
 
 
+@pytest.mark.parametrize("B,N,H,causal,p", [(2, 65, 3, False, 0.15), (3, 197, 2, False, 0.15), (1, 128, 2, False, 0.5),
+                                            (2, 257, 1, False, 0.15), (1, 240, 1, False, 0.3), (1, 200, 2, True, 0.15),
+                                            (1, 384, 1, True, 0.1)])
+def test_flash_attention_dropout(ops, B, N, H, causal, p):
+    """dropout_p of F.scaled_dot_product_attention (transformer.py:28): the kernels regenerate the keep mask from
+    (seed, b*H + h, q, k); the test dumps the same mask through the C ABI and hands it to the oracle, so forward
+    and backward are checked EXACTLY (same tolerance as without dropout), for every attention kernel."""
+    seed = 1234 + N
+    rng = np.random.default_rng(seed)
+    d = H * 64
+    qkv = bf16_round(rng.standard_normal((B, N, 3, H, 64)).astype(np.float32))
+    do = bf16_round(rng.standard_normal((B, N, H, 64)).astype(np.float32))
+    keep = ops.dropout_mask_attn(B, H, N, p, seed, DEV).cpu().numpy().astype(bool)
+    assert abs(keep.mean() - (1 - p)) < 0.02, keep.mean()
+    q, k, v = (np.transpose(qkv[:, :, i], (0, 2, 1, 3)).astype(np.float64) for i in range(3))
+    o_ref, cache = O.sdpa_fwd(q, k, v, causal, keep=keep, dropout_p=p)
+    o, lse = ops.flash_attn_fwd(to_dev(qkv, torch.bfloat16), B, N, H, causal, dropout_p=p, seed=seed)
+    assert_close_bf16(o, np.transpose(o_ref, (0, 2, 1, 3)).reshape(B, N, d), f"attention+dropout fwd N={N}", rel=1.5e-2)
+    dq_ref, dk_ref, dv_ref = O.sdpa_bwd(np.transpose(do, (0, 2, 1, 3)).astype(np.float64), cache)
+    dqkv_ref = np.stack([np.transpose(t, (0, 2, 1, 3)) for t in (dq_ref, dk_ref, dv_ref)], axis=2).reshape(B, N, 3 * d)
+    dqkv = ops.flash_attn_bwd(to_dev(qkv, torch.bfloat16), o, to_dev(do.reshape(B, N, d), torch.bfloat16), lse, B, N, H, causal,
+                              dropout_p=p, seed=seed)
+    got = dqkv.float().cpu().numpy()
+    for i, nm in enumerate(("dq", "dk", "dv")):
+        ref = dqkv_ref[:, :, i * d:(i + 1) * d]
+        err = np.abs(got[:, :, i * d:(i + 1) * d] - ref).max() / (np.abs(ref).max() + 1e-12)
+        assert err < 2e-2, f"attention+dropout bwd {nm} N={N} causal={causal}: {err:.3e}"
+    # a different seed gives a different mask
+    keep2 = ops.dropout_mask_attn(B, H, N, p, seed + 1, DEV).cpu().numpy().astype(bool)
+    assert (keep2 != keep).mean() > 0.05
+
+
+@pytest.mark.parametrize("M,N,K,p", [(1000, 768, 3072, 0.15), (394, 192, 768, 0.5)])
+def test_gemm_dropout_residual(ops, M, N, K, p):
+    """mlp[2] + nn.Dropout + residual (transformer.py:39-40,44) in one epilogue, and its backward cast."""
+    seed = 77 + M
+    rng = np.random.default_rng(seed)
+    x = bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    w = bf16_round(rng.standard_normal((N, K)).astype(np.float32) * 0.05)
+    b = rng.standard_normal(N).astype(np.float32)
+    res = rng.standard_normal((M, N)).astype(np.float32)
+    keep = ops.dropout_mask_rows(M, N, p, seed, DEV).cpu().numpy().astype(np.float64)
+    assert abs(keep.mean() - (1 - p)) < 0.02
+    ref = res + keep / (1 - p) * O.linear_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64))
+    out = ops.gemm_bias_dropout_residual(to_dev(x, torch.bfloat16), to_dev(w, torch.bfloat16), to_dev(b), to_dev(res), p, seed)
+    assert_close_bf16(out, ref, "gemm_bias_dropout_residual", rel=2e-5)
+    dx = rng.standard_normal((M, N)).astype(np.float32)
+    dv = ops.dropout_cast_bf16(to_dev(dx), p, seed)
+    assert_close_bf16(dv, dx * keep / (1 - p), "dropout_cast_bf16", rel=5e-3)
+
+
 # ------------------------------------------------------------------------------------------------ patch embed
 @pytest.mark.parametrize("B,C,H,p,d,extra", [(4, 3, 32, 4, 192, 1), (2, 3, 224, 16, 768, 1), (2, 3, 64, 8, 128, 0),
                                              (3, 64, 8, 1, 64, 5)])

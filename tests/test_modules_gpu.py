@@ -172,6 +172,43 @@ def test_residual_attention_block_matches_reference(golden_dir):
         check_grad(p.grad, g[f"g_{k}"], k)
 
 
+def test_transformer_dropout_semantics():
+    """dropout > 0 (train_vit.py default 0.15): train mode drops attention probabilities and the MLP output; eval
+    mode keeps only SDPA's dropout_p (the reference passes it unconditionally, transformer.py:28); the expectation
+    is preserved and backward uses the forward masks (a finite-difference check along the gradient)."""
+    from b200vit import modules as M
+    torch.manual_seed(0)
+    cfg = M.TransformerConfig(n_layers=2, n_heads=2, n_embd=128, block_size=197, dropout=0.15)
+    m = M.Transformer(cfg).to(DEV)
+    m0 = M.Transformer(M.TransformerConfig(n_layers=2, n_heads=2, n_embd=128, block_size=197, dropout=0.0)).to(DEV)
+    m0.load_state_dict(m.state_dict())
+    x = torch.randn(4, 197, 128, device=DEV)
+    y0 = m0(x)
+    ys = torch.stack([m(x) for _ in range(24)])
+    assert torch.isfinite(ys).all()
+    assert (ys[0] - ys[1]).abs().max() > 1e-3                      # a fresh mask per call
+    # E[dropout(v)] = v: the average over masks approaches the dropout-free output
+    assert rel_l2(ys.mean(0).detach().cpu().numpy(), y0.detach().cpu().numpy()) < 0.08
+    assert rel_l2(ys[0].detach().cpu().numpy(), y0.detach().cpu().numpy()) > rel_l2(ys.mean(0).detach().cpu().numpy(), y0.detach().cpu().numpy())
+    m.eval()
+    e1, e2 = m(x), m(x)
+    assert (e1 - e2).abs().max() > 1e-4                            # SDPA dropout stays on in eval mode
+    m.train()
+    # backward: gradients are finite, and reproducible for a fixed seed stream
+    from b200vit import functional as Fn
+    xg = x.clone().requires_grad_(True)
+    Fn._drop_calls = 1000
+    m(xg).square().mean().backward()
+    g1 = [p.grad.clone() for p in m.parameters()]
+    for p in m.parameters():
+        p.grad = None
+    Fn._drop_calls = 1000
+    m(xg).square().mean().backward()
+    for a, b in zip(g1, [p.grad for p in m.parameters()]):
+        assert torch.isfinite(a).all()
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 1e-3    # same seeds -> same masks (atomics reorder sums)
+
+
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()

@@ -51,6 +51,12 @@ _SIGNATURES = {
     "b200vit_gemm_wgrad_bias": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200vit_flash_attn_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "b200vit_flash_attn_bwd_workspace_size": (_Z, [_I, _I, _I]),
+    "b200vit_flash_attn_fwd_dropout": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, ctypes.c_uint, _P]),
+    "b200vit_flash_attn_bwd_dropout": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, ctypes.c_uint, _P, _Z, _P]),
+    "b200vit_gemm_bias_dropout_residual": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, ctypes.c_uint, _P]),
+    "b200vit_dropout_cast_bf16": (_I, [_P, _P, _L, _I, _F, ctypes.c_uint, _P]),
+    "b200vit_dropout_mask_rows": (_I, [_P, _L, _I, _F, ctypes.c_uint, _P]),
+    "b200vit_dropout_mask_attn": (_I, [_P, _I, _I, _I, _F, ctypes.c_uint, _P]),
     "b200vit_flash_attn_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "b200vit_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
     "b200vit_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),

@@ -53,6 +53,22 @@ def _ready(*params):
             _GRAD_SINK.grad_ready(p)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# Dropout seeds: every dropout site of every forward call draws a fresh 32-bit seed; the masks themselves are pure
+# functions of (seed, coordinates) inside the kernels (csrc/dropout.cuh), so backward only needs the seed.
+# ------------------------------------------------------------------------------------------------------------
+_drop_calls = 0
+
+
+def next_dropout_seed() -> int:
+    global _drop_calls
+    _drop_calls += 1
+    rank = int(__import__("os").environ.get("RANK", "0"))
+    x = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _drop_calls * 0xBF58476D1CE4E5B9 + rank * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 31
+    return (x * 0xD6E8FEB86659FD93 >> 32) & 0xFFFFFFFF
+
+
 def _f32c(t):
     if t is None:
         return None
@@ -79,22 +95,34 @@ class LayerParams:
         self.qkv_w, self.qkv_b, self.fc1_w, self.fc1_b, self.fc2_w, self.fc2_b = qkv_w, qkv_b, fc1_w, fc1_b, fc2_w, fc2_b
 
 
-def layer_forward(x0, P: LayerParams, B, N, H, causal, save):
-    """x0: [B*N, d] fp32 contiguous.  Returns x2 [B*N, d] fp32 and (when save) the tensors backward needs."""
+def layer_forward(x0, P: LayerParams, B, N, H, causal, save, dropout=(0.0, 0.0)):
+    """x0: [B*N, d] fp32 contiguous.  Returns x2 [B*N, d] fp32 and (when save) the tensors backward needs.
+    dropout = (p_attn, p_mlp): dropout_p on the attention probabilities (transformer.py:28, active in eval mode
+    too, as in the reference) and nn.Dropout after mlp[2] (transformer.py:40, training mode only), each with its
+    own fresh seed."""
+    p_attn, p_mlp = dropout
+    seeds = (next_dropout_seed() if p_attn > 0.0 else 0, next_dropout_seed() if p_mlp > 0.0 else 0)
     a, _, mean1, rstd1, _ = ops.layernorm_fwd(x0)
     qkv = ops.gemm_bias(a, bf16_of(P.qkv_w), _f32c(P.qkv_b))
-    o, lse = ops.flash_attn_fwd(qkv, B, N, H, causal, want_lse=save)
+    o, lse = ops.flash_attn_fwd(qkv, B, N, H, causal, want_lse=save, dropout_p=p_attn, seed=seeds[0])
     b, _, mean2, rstd2, x1 = ops.layernorm_fwd(x0, add=o.view(B * N, -1), want_x_out=True)
     g, u = ops.gemm_bias_gelu(b, bf16_of(P.fc1_w), _f32c(P.fc1_b))  # u := GELU'(pre-activation)
-    x2 = ops.gemm_bias_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1)
-    saved = (x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g) if save else None
+    if p_mlp > 0.0:
+        x2 = ops.gemm_bias_dropout_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1, p_mlp, seeds[1])
+    else:
+        x2 = ops.gemm_bias_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1)
+    saved = (x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g, seeds) if save else None
     return x2, saved
 
 
-def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_dx=True):
+def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_dx=True, dropout=(0.0, 0.0)):
     """dx2: [B*N, d] fp32 (dx2_bf16: optional bf16 copy).  Returns (dx0, dx0_bf16, grads in LayerParams order)."""
-    x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g = saved
-    dv = dx2_bf16 if dx2_bf16 is not None else ops.cast_bf16(dx2)
+    x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g, seeds = saved
+    p_attn, p_mlp = dropout
+    if p_mlp > 0.0:
+        dv = ops.dropout_cast_bf16(dx2, p_mlp, seeds[1])   # gradient through nn.Dropout, same mask as forward
+    else:
+        dv = dx2_bf16 if dx2_bf16 is not None else ops.cast_bf16(dx2)
     d_fc2_w, d_fc2_b = ops.gemm_wgrad(dv, g, out=_slot(P.fc2_w), bias_out=_slot(P.fc2_b), want_bias=True)
     _ready(P.fc2_w, P.fc2_b)
     du = ops.gemm_dgrad_dgelu(dv, bf16_of(P.fc2_w), u)
@@ -102,7 +130,7 @@ def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_d
     _ready(P.fc1_w, P.fc1_b)
     db = ops.gemm_dgrad(du, bf16_of(P.fc1_w))
     dx1, dx1_bf16, _, _ = ops.layernorm_bwd(db, x1, mean2, rstd2, dres=dx2, want_bf16=True)
-    dqkv = ops.flash_attn_bwd(qkv, o, dx1_bf16.view(B, N, -1), lse, B, N, H, causal).view(B * N, -1)
+    dqkv = ops.flash_attn_bwd(qkv, o, dx1_bf16.view(B, N, -1), lse, B, N, H, causal, dropout_p=p_attn, seed=seeds[0]).view(B * N, -1)
     d_qkv_w, d_qkv_b = ops.gemm_wgrad(dqkv, a, out=_slot(P.qkv_w), bias_out=_slot(P.qkv_b), want_bias=True)
     _ready(P.qkv_w, P.qkv_b)
     dx0 = dx0_bf16 = None
@@ -118,7 +146,7 @@ class TransformerStackFn(torch.autograd.Function):
     gradient from layer to layer without an extra cast pass."""
 
     @staticmethod
-    def forward(ctx, x, n_heads, causal, *params):
+    def forward(ctx, x, n_heads, causal, dropout, *params):  # dropout = (p_attention, p_mlp)
         B, N, d = x.shape
         n_layers = len(params) // 6
         layers = [LayerParams(*params[6 * i:6 * i + 6]) for i in range(n_layers)]
@@ -126,11 +154,12 @@ class TransformerStackFn(torch.autograd.Function):
         h = _as_rows_f32(x).view(B * N, d)
         saved_all = []
         for P in layers:
-            h, saved = layer_forward(h, P, B, N, n_heads, causal, need_grad)
+            h, saved = layer_forward(h, P, B, N, n_heads, causal, need_grad, dropout)
             saved_all.append(saved)
         ctx.layers = layers
         ctx.saved_all = saved_all
         ctx.dims = (B, N, d, n_heads, causal)
+        ctx.dropout = dropout
         ctx.x_needs_grad = x.requires_grad
         return h.view(B, N, d)
 
@@ -143,27 +172,29 @@ class TransformerStackFn(torch.autograd.Function):
         n = len(ctx.layers)
         for i in range(n - 1, -1, -1):
             need_dx = i > 0 or ctx.x_needs_grad
-            dx, dx_bf16, g = layer_backward(dx, dx_bf16, ctx.saved_all[i], ctx.layers[i], B, N, H, causal, need_dx)
+            dx, dx_bf16, g = layer_backward(dx, dx_bf16, ctx.saved_all[i], ctx.layers[i], B, N, H, causal, need_dx, ctx.dropout)
             ctx.saved_all[i] = None  # free activations as we go
             grads.append(g)
         flat = []
         for g in reversed(grads):
             flat.extend(g)
         ctx.saved_all = None
-        return (dx.view(B, N, d) if dx is not None else None, None, None, *flat)
+        return (dx.view(B, N, d) if dx is not None else None, None, None, None, *flat)
 
 
 class AttentionFn(torch.autograd.Function):
     """transformer.Attention.forward on its own (transformer.py:26-29): qkv Linear + SDPA, no out-proj."""
 
     @staticmethod
-    def forward(ctx, x, qkv_w, qkv_b, n_heads, causal):
+    def forward(ctx, x, qkv_w, qkv_b, n_heads, causal, dropout=0.0):
         B, N, d = x.shape
+        seed = next_dropout_seed() if dropout > 0.0 else 0
         a = ops.cast_bf16(_as_rows_f32(x).view(B * N, d))
         qkv = ops.gemm_bias(a, bf16_of(qkv_w), _f32c(qkv_b))
-        o, lse = ops.flash_attn_fwd(qkv, B, N, n_heads, causal)
+        o, lse = ops.flash_attn_fwd(qkv, B, N, n_heads, causal, dropout_p=dropout, seed=seed)
         ctx.saved = (a, qkv, o, lse, qkv_w)
         ctx.dims = (B, N, d, n_heads, causal)
+        ctx.drop = (dropout, seed)
         return o.float()
 
     @staticmethod
@@ -171,10 +202,10 @@ class AttentionFn(torch.autograd.Function):
         a, qkv, o, lse, qkv_w = ctx.saved
         B, N, d, H, causal = ctx.dims
         do16 = ops.cast_bf16(_as_rows_f32(do).view(B * N, d)).view(B, N, d)
-        dqkv = ops.flash_attn_bwd(qkv, o, do16, lse, B, N, H, causal).view(B * N, -1)
+        dqkv = ops.flash_attn_bwd(qkv, o, do16, lse, B, N, H, causal, dropout_p=ctx.drop[0], seed=ctx.drop[1]).view(B * N, -1)
         dw, db = ops.gemm_wgrad(dqkv, a, want_bias=True)
         dx = ops.gemm_dgrad(dqkv, bf16_of(qkv_w)).float().view(B, N, d)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -44,9 +44,15 @@ def _check_supported(module):
     if module.head_dim != 64:
         raise NotImplementedError(f"b200vit attention kernels are built for head_dim 64 (got {module.head_dim}); "
                                   "every shipped reference config uses 64 (transformer.py:56-58)")
-    if module.dropout != 0.0:
-        raise NotImplementedError("b200vit: dropout > 0 is not implemented on the fused path yet (parity is only "
-                                  "defined at dropout = 0, SURVEY.md §0.6); construct the config with dropout=0.0")
+    if not (0.0 <= float(module.dropout) < 1.0):
+        raise ValueError(f"dropout must be in [0, 1), got {module.dropout}")
+
+
+def _dropout_pair(module):
+    """(p_attention, p_mlp): SDPA's dropout_p is applied whether or not the module is training (transformer.py:28
+    passes self.dropout unconditionally); nn.Dropout after mlp[2] (transformer.py:40) only in training mode."""
+    p = float(module.dropout)
+    return (p, p if module.training else 0.0)
 
 
 class Attention(nn.Module):
@@ -64,7 +70,8 @@ class Attention(nn.Module):
         _check_supported(self)
 
     def forward(self, x):
-        return Fn.AttentionFn.apply(x, self.qkv.weight, self.qkv.bias, self.n_heads, bool(self.causal))
+        # like the reference (transformer.py:28) the attention dropout is active regardless of self.training
+        return Fn.AttentionFn.apply(x, self.qkv.weight, self.qkv.bias, self.n_heads, bool(self.causal), float(self.dropout))
 
 
 class TransformerLayer(nn.Module):
@@ -86,7 +93,7 @@ class TransformerLayer(nn.Module):
                 self.mlp[2].weight, self.mlp[2].bias)
 
     def forward(self, x):
-        return Fn.TransformerStackFn.apply(x, self.n_heads, bool(self.causal), *self._params())
+        return Fn.TransformerStackFn.apply(x, self.n_heads, bool(self.causal), _dropout_pair(self), *self._params())
 
 
 class Transformer(nn.Module):
@@ -101,7 +108,7 @@ class Transformer(nn.Module):
         params = []
         for layer in self.layers:
             params.extend(layer._params())
-        return Fn.TransformerStackFn.apply(x, self.n_heads, bool(self.causal), *params)
+        return Fn.TransformerStackFn.apply(x, self.n_heads, bool(self.causal), _dropout_pair(self), *params)
 
 
 def S(**kwargs): return TransformerConfig(n_layers=6, n_heads=8, n_embd=512, **kwargs)

@@ -19,7 +19,7 @@ launch_count = 0  # number of C-ABI compute calls issued (bench.py reports it as
 
 
 # kernels launched per C-ABI call (memsets not counted); everything else launches exactly one kernel
-_KERNELS_PER_CALL = {"b200vit_flash_attn_bwd": 2, "b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3}
+_KERNELS_PER_CALL = {"b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3}
 
 _prof = None  # list of (start_event, end_event, flops) while profile_gemms() is active
 
@@ -97,6 +97,37 @@ def gemm_bias_residual(x, w, bias, resid):
     return out
 
 
+def gemm_bias_dropout_residual(x, w, bias, resid, p, seed):
+    """out = resid + dropout_p(x w^T + bias) (fp32); the keep mask is a function of (seed, row, column)."""
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=x.device, dtype=F32)
+    _call("b200vit_gemm_bias_dropout_residual", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(_chk(resid, F32, "resid")), ptr(out),
+          M, N, K, float(p), int(seed) & 0xFFFFFFFF, stream_ptr(), flops=2.0 * M * N * K)
+    return out
+
+
+def dropout_cast_bf16(x, p, seed):
+    """bf16(x * keep / (1 - p)) for x [M, d] fp32: the backward of the dropout above, fused with the bf16 cast."""
+    d = x.shape[-1]
+    M = x.numel() // d
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _call("b200vit_dropout_cast_bf16", x, ptr(_chk(x, F32, "x")), ptr(out), M, d, float(p), int(seed) & 0xFFFFFFFF, stream_ptr())
+    return out
+
+
+def dropout_mask_rows(M, d, p, seed, device):
+    out = torch.empty(M, d, device=device, dtype=torch.uint8)
+    _call("b200vit_dropout_mask_rows", out, ptr(out), M, d, float(p), int(seed) & 0xFFFFFFFF, stream_ptr())
+    return out
+
+
+def dropout_mask_attn(B, H, N, p, seed, device):
+    out = torch.empty(B, H, N, N, device=device, dtype=torch.uint8)
+    _call("b200vit_dropout_mask_attn", out, ptr(out), B, H, N, float(p), int(seed) & 0xFFFFFFFF, stream_ptr())
+    return out
+
+
 def gemm_bias_f32(x, w, bias=None):
     M, K = x.shape
     N = w.shape[0]
@@ -142,21 +173,23 @@ def gemm_wgrad(dy, x, out=None, accumulate=False, bias_out=None, want_bias=False
 
 
 # ---------------------------------------------------------------- attention
-def flash_attn_fwd(qkv, B, N, H, causal=False, want_lse=True, seq_first=False):
+def flash_attn_fwd(qkv, B, N, H, causal=False, want_lse=True, seq_first=False, dropout_p=0.0, seed=0):
     d = H * 64
     assert qkv.numel() == B * N * 3 * d
     o = torch.empty((N, B, d) if seq_first else (B, N, d), device=qkv.device, dtype=BF16)
     lse = torch.empty(B, H, N, device=qkv.device, dtype=F32) if want_lse else None
-    _call("b200vit_flash_attn_fwd", qkv, ptr(_chk(qkv, BF16, "qkv")), ptr(o), ptr(lse), B, N, H, 1 if causal else 0, 1 if seq_first else 0, stream_ptr())
+    _call("b200vit_flash_attn_fwd_dropout", qkv, ptr(_chk(qkv, BF16, "qkv")), ptr(o), ptr(lse), B, N, H, 1 if causal else 0, 1 if seq_first else 0,
+          float(dropout_p), int(seed) & 0xFFFFFFFF, stream_ptr())
     return o, lse
 
 
-def flash_attn_bwd(qkv, o, d_o, lse, B, N, H, causal=False, seq_first=False):
+def flash_attn_bwd(qkv, o, d_o, lse, B, N, H, causal=False, seq_first=False, dropout_p=0.0, seed=0):
     d = H * 64
     dqkv = torch.empty((N, B, 3 * d) if seq_first else (B, N, 3 * d), device=qkv.device, dtype=BF16)
     ws = torch.empty(B * N * d, device=qkv.device, dtype=F32)
-    _call("b200vit_flash_attn_bwd", qkv, ptr(_chk(qkv, BF16, "qkv")), ptr(_chk(o, BF16, "o")), ptr(_chk(d_o, BF16, "d_o")), ptr(_chk(lse, F32, "lse")),
-          ptr(dqkv), B, N, H, 1 if causal else 0, 1 if seq_first else 0, ptr(ws), ws.numel() * 4, stream_ptr())
+    _call("b200vit_flash_attn_bwd_dropout", qkv, ptr(_chk(qkv, BF16, "qkv")), ptr(_chk(o, BF16, "o")), ptr(_chk(d_o, BF16, "d_o")), ptr(_chk(lse, F32, "lse")),
+          ptr(dqkv), B, N, H, 1 if causal else 0, 1 if seq_first else 0, float(dropout_p), int(seed) & 0xFFFFFFFF,
+          ptr(ws), ws.numel() * 4, stream_ptr())
     return dqkv
 
 

@@ -17,6 +17,7 @@
 //   dV += P^T dO, dK += dS^T Q (accumulated in TMEM), dQ = dS K (fp32 atomics, converted afterwards).
 #include "../../include/b200vit.h"
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace b200 {
 
@@ -41,6 +42,9 @@ struct AttnParams {
   const __nv_bfloat16* do_in;  // [B, N, d]
   float* dq_acc;               // [B, N, d] fp32, zeroed
   __nv_bfloat16* dqkv;         // [B, N, 3d]
+  // dropout on the attention probabilities (dropout_p of SDPA, transformer.py:28); drop_thr == 0: none
+  uint32_t drop_seed, drop_thr;
+  float drop_r;                // 1 / (1 - p)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -255,6 +259,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
             if (!(key + 1 < p.N && (!CAUSAL || key + 1 <= q))) p1 = 0.f;
           }
           rowsum += p0 + p1;
+          if (p.drop_thr != 0) {  // the row sum (softmax denominator) is taken before dropout
+            const int key = j * AT_BK + c * 32 + i;
+            const uint32_t h = drop_hash_attn(p.drop_seed, (uint32_t)(b * p.H + hh), (uint32_t)q, (uint32_t)(key >> 1));
+            if (!drop_keep(h, 0, p.drop_thr)) p0 = 0.f;
+            if (!drop_keep(h, 1, p.drop_thr)) p1 = 0.f;
+          }
           w[i >> 1] = pack_bf16(p0, p1);
         }
         store_operand_chunk(smem + FwdSmem::P, r, c, w);
@@ -280,7 +290,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
       }
     }
     if (q < p.N) {
-      const float inv = 1.0f / l;
+      const float inv = p.drop_r / l;   // kept probabilities are scaled by 1 / (1 - p)
       __nv_bfloat16* orow = p.o + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -381,6 +391,7 @@ struct FwdShortSmem {
 
 __device__ __forceinline__ void tmem_st16_packed(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st16(taddr, v); }
 
+template <bool DROP>
 __global__ void __launch_bounds__(AS_THREADS, 1)
 attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
                       const AttnParams p) {
@@ -507,6 +518,8 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
       int n = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
         const int b = u / p.H, hh = u - b * p.H;
+        const uint32_t bh = (uint32_t)u;   // == b * H + hh
+        (void)bh;
         mbar_wait(&s_full[t], n & 1, 44);
         tc_fence_after();
         float l = 0.f, m2 = 0.f;
@@ -549,9 +562,14 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 #pragma unroll
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), p.scale_log2e, -m2));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(x[i + 1]), p.scale_log2e, -m2));
+                float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), p.scale_log2e, -m2));
+                float p1 = ex2_approx(fmaf(__uint_as_float(x[i + 1]), p.scale_log2e, -m2));
                 l += p0 + p1;
+                if constexpr (DROP) {  // the denominator is taken before dropout; 1 / (1 - p) is applied to O
+                  const uint32_t h = drop_hash_attn(p.drop_seed, bh, (uint32_t)q, (uint32_t)((c * 32 + i) >> 1));
+                  if (!drop_keep(h, 0, p.drop_thr)) p0 = 0.f;
+                  if (!drop_keep(h, 1, p.drop_thr)) p1 = 0.f;
+                }
                 w[i >> 1] = pack_bf16(p0, p1);
               }
             } else {
@@ -562,6 +580,11 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 if (c * 32 + i >= p.N) p0 = 0.f;
                 if (c * 32 + i + 1 >= p.N) p1 = 0.f;
                 l += p0 + p1;
+                if constexpr (DROP) {
+                  const uint32_t h = drop_hash_attn(p.drop_seed, bh, (uint32_t)q, (uint32_t)((c * 32 + i) >> 1));
+                  if (!drop_keep(h, 0, p.drop_thr)) p0 = 0.f;
+                  if (!drop_keep(h, 1, p.drop_thr)) p1 = 0.f;
+                }
                 w[i >> 1] = pack_bf16(p0, p1);
               }
             }
@@ -589,6 +612,11 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
               if (nch * 32 + i >= p.N) p0 = 0.f;
               if (nch * 32 + i + 1 >= p.N) p1 = 0.f;
               l += p0 + p1;
+              if constexpr (DROP) {
+                const uint32_t h = drop_hash_attn(p.drop_seed, bh, (uint32_t)q, (uint32_t)((nch * 32 + i) >> 1));
+                if (!drop_keep(h, 0, p.drop_thr)) p0 = 0.f;
+                if (!drop_keep(h, 1, p.drop_thr)) p1 = 0.f;
+              }
               w[i >> 1] = pack_bf16(p0, p1);
             }
 #pragma unroll
@@ -606,7 +634,7 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         tc_fence_after();
         if (warp_has_rows) {
           // normalise, stage as bf16 (swizzled) and leave through one TMA store per warp
-          bwd2_store_tile(tS + 128, 1.0f / l, smem + FwdShortSmem::OST + t * AT_TILE_BYTES + wq * 4096, true, &tm_o,
+          bwd2_store_tile(tS + 128, (DROP ? p.drop_r : 1.0f) / l, smem + FwdShortSmem::OST + t * AT_TILE_BYTES + wq * 4096, true, &tm_o,
                           hh * AT_HD, t * 128 + wq * 32, b, lane);
           if (q < p.N && p.lse != nullptr) p.lse[((long long)b * p.H + hh) * p.N + q] = m2 * LN2 + logf(l);
         }
@@ -769,8 +797,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             const int key = k0 + c * 32 + i + e;
             const bool ok = qv && key < p.N && (!CAUSAL || key <= q);
             const float pe = ok ? ex2_approx(fmaf(__uint_as_float(s[i + e]), p.scale_log2e, -lse2)) : 0.f;
-            pv[e] = pe;
-            dv[e] = pe * (__uint_as_float(dp[i + e]) - Dq) * p.scale;
+            float pk = pe, dpe = __uint_as_float(dp[i + e]);
+            if (p.drop_thr != 0) {  // dV uses the dropped probabilities, dP = mask / (1 - p) * (dO V^T)
+              const bool keep = drop_keep(drop_hash_attn(p.drop_seed, (uint32_t)(b * p.H + hh), (uint32_t)q, (uint32_t)(key >> 1)),
+                                          key & 1, p.drop_thr);
+              pk = keep ? pe : 0.f;
+              dpe = keep ? dpe * p.drop_r : 0.f;
+            }
+            pv[e] = pk;
+            dv[e] = pe * (dpe - Dq) * p.scale;
           }
           wp[i >> 1] = pack_bf16(pv[0], pv[1]);
           wd[i >> 1] = pack_bf16(dv[0], dv[1]);
@@ -812,14 +847,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_off + c * 32, v);
         tmem_ld_wait();
         if (key < p.N) {
+          const float sc = which == 1 ? p.drop_r : 1.0f;   // dV = (mask P / (1 - p))^T dO
           __nv_bfloat16* dst = p.dqkv + ((long long)b * p.sb + key * p.sn) * 3 * p.d + (which + 1) * p.d + hh * AT_HD + c * 32;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint4 w;
-            w.x = pack_bf16(__uint_as_float(v[i * 8 + 0]), __uint_as_float(v[i * 8 + 1]));
-            w.y = pack_bf16(__uint_as_float(v[i * 8 + 2]), __uint_as_float(v[i * 8 + 3]));
-            w.z = pack_bf16(__uint_as_float(v[i * 8 + 4]), __uint_as_float(v[i * 8 + 5]));
-            w.w = pack_bf16(__uint_as_float(v[i * 8 + 6]), __uint_as_float(v[i * 8 + 7]));
+            w.x = pack_bf16(__uint_as_float(v[i * 8 + 0]) * sc, __uint_as_float(v[i * 8 + 1]) * sc);
+            w.y = pack_bf16(__uint_as_float(v[i * 8 + 2]) * sc, __uint_as_float(v[i * 8 + 3]) * sc);
+            w.z = pack_bf16(__uint_as_float(v[i * 8 + 4]) * sc, __uint_as_float(v[i * 8 + 5]) * sc);
+            w.w = pack_bf16(__uint_as_float(v[i * 8 + 6]) * sc, __uint_as_float(v[i * 8 + 7]) * sc);
             reinterpret_cast<uint4*>(dst)[i] = w;
           }
         }
@@ -983,8 +1019,15 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
                 const int key = k0 + c * 32 + e2 + e;
                 const bool ok = qv && key < p.N && (!CAUSAL || key <= q);
                 const float pe = ok ? ex2_approx(fmaf(__uint_as_float(s[e2 + e]), p.scale_log2e, -my_lse)) : 0.f;
-                pv[e] = pe;
-                dv[e] = pe * (__uint_as_float(dp[e2 + e]) - my_D) * p.scale;
+                float pk = pe, dpe = __uint_as_float(dp[e2 + e]);
+                if (p.drop_thr != 0) {
+                  const bool keep = drop_keep(drop_hash_attn(p.drop_seed, (uint32_t)(b * p.H + hh), (uint32_t)q, (uint32_t)(key >> 1)),
+                                              key & 1, p.drop_thr);
+                  pk = keep ? pe : 0.f;
+                  dpe = keep ? dpe * p.drop_r : 0.f;
+                }
+                pv[e] = pk;
+                dv[e] = pe * (dpe - my_D) * p.scale;
               }
               wp[e2 >> 1] = pack_bf16(pv[0], pv[1]);
               wd[e2 >> 1] = pack_bf16(dv[0], dv[1]);
@@ -1009,14 +1052,15 @@ attn_bwd_small_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_off + c * 32, v);
           tmem_ld_wait();
           if (key < p.N) {
+            const float sc = which == 1 ? p.drop_r : 1.0f;   // dV = (mask P / (1 - p))^T dO
             __nv_bfloat16* dst = p.dqkv + ((long long)b * p.sb + key * p.sn) * 3 * p.d + (which + 1) * p.d + hh * AT_HD + c * 32;
 #pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
               uint4 w;
-              w.x = pack_bf16(__uint_as_float(v[i4 * 8 + 0]), __uint_as_float(v[i4 * 8 + 1]));
-              w.y = pack_bf16(__uint_as_float(v[i4 * 8 + 2]), __uint_as_float(v[i4 * 8 + 3]));
-              w.z = pack_bf16(__uint_as_float(v[i4 * 8 + 4]), __uint_as_float(v[i4 * 8 + 5]));
-              w.w = pack_bf16(__uint_as_float(v[i4 * 8 + 6]), __uint_as_float(v[i4 * 8 + 7]));
+              w.x = pack_bf16(__uint_as_float(v[i4 * 8 + 0]) * sc, __uint_as_float(v[i4 * 8 + 1]) * sc);
+              w.y = pack_bf16(__uint_as_float(v[i4 * 8 + 2]) * sc, __uint_as_float(v[i4 * 8 + 3]) * sc);
+              w.z = pack_bf16(__uint_as_float(v[i4 * 8 + 4]) * sc, __uint_as_float(v[i4 * 8 + 5]) * sc);
+              w.w = pack_bf16(__uint_as_float(v[i4 * 8 + 6]) * sc, __uint_as_float(v[i4 * 8 + 7]) * sc);
               reinterpret_cast<uint4*>(dst)[i4] = w;
             }
           }
@@ -1097,6 +1141,7 @@ struct Bwd2Layout {
   }
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(AB2_THREADS, 1)
 attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid_constant__ CUtensorMap tm_qkv_b,
                       const __grid_constant__ CUtensorMap tm_do_a, const __grid_constant__ CUtensorMap tm_do_b,
@@ -1303,6 +1348,8 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
         for (int j = 0; j < nt; ++j, ++cc) {
           const int key_local = j * 128 + r;            // row in the packed operands / dS^T slabs
           const bool warp_has_keys = j * 128 + wq * 32 < ncols;
+          const uint32_t bh = (uint32_t)u, kpair = (uint32_t)(key_local >> 1), kodd = (uint32_t)(key_local & 1);
+          (void)bh; (void)kpair; (void)kodd;
           mbar_wait(&sdp_full[i], cc & 1, 95);
           tc_fence_after();
           if (warp_has_keys) {
@@ -1320,10 +1367,23 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
                   const float p1 = ex2_approx(fmaf(__uint_as_float(sv[e4 * 4 + 1]), p.scale_log2e, a.y));
                   const float p2 = ex2_approx(fmaf(__uint_as_float(sv[e4 * 4 + 2]), p.scale_log2e, a.z));
                   const float p3 = ex2_approx(fmaf(__uint_as_float(sv[e4 * 4 + 3]), p.scale_log2e, a.w));
-                  wp[e4 * 2 + 0] = pack_bf16(p0, p1);
-                  wp[e4 * 2 + 1] = pack_bf16(p2, p3);
-                  wd[e4 * 2 + 0] = pack_bf16(p0 * (__uint_as_float(dv[e4 * 4 + 0]) - dd.x), p1 * (__uint_as_float(dv[e4 * 4 + 1]) - dd.y));
-                  wd[e4 * 2 + 1] = pack_bf16(p2 * (__uint_as_float(dv[e4 * 4 + 2]) - dd.z), p3 * (__uint_as_float(dv[e4 * 4 + 3]) - dd.w));
+                  float g0 = __uint_as_float(dv[e4 * 4 + 0]), g1 = __uint_as_float(dv[e4 * 4 + 1]);
+                  float g2 = __uint_as_float(dv[e4 * 4 + 2]), g3 = __uint_as_float(dv[e4 * 4 + 3]);
+                  float k0 = p0, k1 = p1, k2 = p2, k3 = p3;   // probabilities as used by dV (after dropout)
+                  if constexpr (DROP) {  // this thread's key is fixed, the query index runs: one hash per element
+                    const uint32_t q0 = (uint32_t)(i * 128 + c * 32 + e4 * 4);
+                    const bool m0 = drop_keep(drop_hash_attn(p.drop_seed, bh, q0 + 0, kpair), kodd, p.drop_thr);
+                    const bool m1 = drop_keep(drop_hash_attn(p.drop_seed, bh, q0 + 1, kpair), kodd, p.drop_thr);
+                    const bool m2 = drop_keep(drop_hash_attn(p.drop_seed, bh, q0 + 2, kpair), kodd, p.drop_thr);
+                    const bool m3 = drop_keep(drop_hash_attn(p.drop_seed, bh, q0 + 3, kpair), kodd, p.drop_thr);
+                    k0 = m0 ? p0 : 0.f; k1 = m1 ? p1 : 0.f; k2 = m2 ? p2 : 0.f; k3 = m3 ? p3 : 0.f;
+                    g0 = m0 ? g0 * p.drop_r : 0.f; g1 = m1 ? g1 * p.drop_r : 0.f;
+                    g2 = m2 ? g2 * p.drop_r : 0.f; g3 = m3 ? g3 * p.drop_r : 0.f;
+                  }
+                  wp[e4 * 2 + 0] = pack_bf16(k0, k1);
+                  wp[e4 * 2 + 1] = pack_bf16(k2, k3);
+                  wd[e4 * 2 + 0] = pack_bf16(p0 * (g0 - dd.x), p1 * (g1 - dd.y));
+                  wd[e4 * 2 + 1] = pack_bf16(p2 * (g2 - dd.z), p3 * (g3 - dd.w));
                 } else {
                   wp[e4 * 2 + 0] = 0u; wp[e4 * 2 + 1] = 0u; wd[e4 * 2 + 0] = 0u; wd[e4 * 2 + 1] = 0u;
                 }
@@ -1377,7 +1437,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
             const bool wr = key_local < ncols;
             const int row0 = j * 128 + wq * 32;
             if (nt == 1 || i == 0)   // dV_j -> staged in the (dead) V_j rows
-              bwd2_store_tile(tmem_base + 64 + lane_off, 1.0f, smem + L.sV + row0 * 128, wr, &tm_out,
+              bwd2_store_tile(tmem_base + 64 + lane_off, DROP ? p.drop_r : 1.0f, smem + L.sV + row0 * 128, wr, &tm_out,
                               2 * p.d + hh * AT_HD, row0, b, lane);
             if (nt == 1 || i == 1)   // dK_j -> staging tile X
               bwd2_store_tile(tmem_base + 320 + lane_off, p.scale, smem + L.sX + wq * 4096, wr, &tm_out,
@@ -1441,7 +1501,13 @@ extern "C" {
 
 int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int causal,
                            int seq_first, void* stream) {
+  return b200vit_flash_attn_fwd_dropout(qkv, o, lse, B, N, H, causal, seq_first, 0.f, 0u, stream);
+}
+
+int b200vit_flash_attn_fwd_dropout(const void* qkv, void* o, float* lse, int B, int N, int H, int causal,
+                                   int seq_first, float dropout_p, unsigned int seed, void* stream) {
   B200_REQUIRE(qkv && o, "flash_attn_fwd: null pointer");
+  B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "flash_attn_fwd: dropout_p must be in [0, 1)");
   B200_REQUIRE(B > 0 && N > 0 && H > 0, "flash_attn_fwd: bad sizes");
   const int d = H * AT_HD;
   CUtensorMap tm;
@@ -1452,17 +1518,20 @@ int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, i
   p.sb = seq_first ? 1 : N; p.sn = seq_first ? B : 1;
   p.scale = 0.125f; p.scale_log2e = 0.125f * LOG2E;
   p.o = (__nv_bfloat16*)o; p.lse = lse;
+  p.drop_seed = seed; p.drop_thr = dropout_p > 0.f ? drop_threshold(dropout_p) : 0u; p.drop_r = 1.0f / (1.0f - dropout_p);
   dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
   cudaStream_t st = (cudaStream_t)stream;
   if (!causal && N <= 256 && g_debug[7] == 0) {
     // short sequences: persistent kernel, whole head resident, exact single-shot softmax, P in TMEM
-    B200_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdShortSmem::TOTAL));
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdShortSmem::TOTAL));
+    B200_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdShortSmem::TOTAL));
     CUtensorMap tm_o;
     rc = make_tmap_bnd(&tm_o, o, B, N, d, seq_first, 32);
     if (rc != OK) return rc;
     const int units = B * H;
     const int g = units < num_sms() ? units : num_sms();
-    attn_fwd_short_kernel<<<g, AS_THREADS, FwdShortSmem::TOTAL, st>>>(tm, tm_o, p);
+    if (p.drop_thr != 0) attn_fwd_short_kernel<true><<<g, AS_THREADS, FwdShortSmem::TOTAL, st>>>(tm, tm_o, p);
+    else                 attn_fwd_short_kernel<false><<<g, AS_THREADS, FwdShortSmem::TOTAL, st>>>(tm, tm_o, p);
     B200_CUDA(cudaGetLastError());
     return OK;
   }
@@ -1484,7 +1553,15 @@ size_t b200vit_flash_attn_bwd_workspace_size(int B, int N, int H) {
 int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
                            int B, int N, int H, int causal, int seq_first, void* workspace,
                            size_t workspace_bytes, void* stream) {
+  return b200vit_flash_attn_bwd_dropout(qkv, o, d_o, lse, dqkv, B, N, H, causal, seq_first, 0.f, 0u, workspace,
+                                        workspace_bytes, stream);
+}
+
+int b200vit_flash_attn_bwd_dropout(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
+                                   int B, int N, int H, int causal, int seq_first, float dropout_p,
+                                   unsigned int seed, void* workspace, size_t workspace_bytes, void* stream) {
   B200_REQUIRE(qkv && o && d_o && lse && dqkv && workspace, "flash_attn_bwd: null pointer");
+  B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "flash_attn_bwd: dropout_p must be in [0, 1)");
   B200_REQUIRE(workspace_bytes >= b200vit_flash_attn_bwd_workspace_size(B, N, H), "flash_attn_bwd: workspace too small");
   const int d = H * AT_HD;
   CUtensorMap tm_qkv, tm_do;
@@ -1500,6 +1577,7 @@ int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
   p.lse = const_cast<float*>(lse);
   p.o_in = (const __nv_bfloat16*)o; p.do_in = (const __nv_bfloat16*)d_o;
   p.dq_acc = (float*)workspace; p.dqkv = (__nv_bfloat16*)dqkv;
+  p.drop_seed = seed; p.drop_thr = dropout_p > 0.f ? drop_threshold(dropout_p) : 0u; p.drop_r = 1.0f / (1.0f - dropout_p);
   if (!causal && N <= 208 && g_debug[7] == 0) {
     // short sequences, transposed formulation: persistent, whole head resident, P^T kept in TMEM
     const int ncols = ((N + 15) / 16) * 16, nt = (N + 127) / 128;
@@ -1520,10 +1598,12 @@ int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
     rc = make_tmap_bnd(&tout, dqkv, B, N, 3 * d, seq_first, 32);
     if (rc != OK) return rc;
     const Bwd2Layout L(ncols, nt);
-    B200_CUDA(cudaFuncSetAttribute(attn_bwd_short_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.alloc_bytes(nt)));
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_short_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.alloc_bytes(nt)));
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_short_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.alloc_bytes(nt)));
     const int units = B * H;
     const int g = units < num_sms() ? units : num_sms();
-    attn_bwd_short_kernel<<<g, AB2_THREADS, L.alloc_bytes(nt), st>>>(qa, qb, da, db, tout, p);
+    if (p.drop_thr != 0) attn_bwd_short_kernel<true><<<g, AB2_THREADS, L.alloc_bytes(nt), st>>>(qa, qb, da, db, tout, p);
+    else                 attn_bwd_short_kernel<false><<<g, AB2_THREADS, L.alloc_bytes(nt), st>>>(qa, qb, da, db, tout, p);
     B200_CUDA(cudaGetLastError());
     return OK;
   }

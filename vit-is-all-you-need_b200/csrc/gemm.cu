@@ -108,7 +108,7 @@ static int check_common(const void* a, const void* b, const void* c, int M, int 
 static EpiParams make_ep(void* out, long long ldo) {
   EpiParams ep;
   ep.out = out; ep.ldo = ldo; ep.bias = nullptr;
-  ep.aux = nullptr; ep.ldaux = 0; ep.pos = nullptr; ep.P = 1; ep.T = 1; ep.extra = 0; ep.colsum = nullptr;
+  ep.aux = nullptr; ep.ldaux = 0; ep.pos = nullptr; ep.P = 1; ep.T = 1; ep.extra = 0; ep.colsum = nullptr; ep.drop_seed = 0; ep.drop_thr = 0; ep.drop_r = 1.0f;
   return ep;
 }
 
@@ -173,6 +173,19 @@ int b200vit_gemm_bias_residual(const void* x, const void* w, const float* bias, 
   EpiParams ep = make_ep(out, N);
   ep.bias = bias; ep.aux = resid; ep.ldaux = N;
   return launch_bn<false, false, EPI_RESID_F32>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
+}
+
+int b200vit_gemm_bias_dropout_residual(const void* x, const void* w, const float* bias, const float* resid,
+                                       float* out, int M, int N, int K, float p, unsigned int seed, void* stream) {
+  if (p <= 0.f) return b200vit_gemm_bias_residual(x, w, bias, resid, out, M, N, K, stream);
+  int rc = check_common(x, w, out, M, N, K);
+  if (rc) return rc;
+  B200_REQUIRE(resid != nullptr, "gemm_bias_dropout_residual: resid is null");
+  B200_REQUIRE(p < 1.f, "gemm_bias_dropout_residual: p must be in [0, 1)");
+  EpiParams ep = make_ep(out, N);
+  ep.bias = bias; ep.aux = resid; ep.ldaux = N;
+  ep.drop_seed = seed; ep.drop_thr = drop_threshold(p); ep.drop_r = 1.0f / (1.0f - p);
+  return launch_bn<false, false, EPI_DROP_RESID_F32>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
 }
 
 int b200vit_gemm_bias_f32(const void* x, const void* w, const float* bias, float* out, int M, int N,

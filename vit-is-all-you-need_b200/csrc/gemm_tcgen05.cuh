@@ -28,6 +28,7 @@
 // both CTAs; both CTAs' epilogue warps arrive on the leader's "accumulator drained" barrier.
 #pragma once
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace b200 {
 
@@ -55,10 +56,12 @@ enum EpiKind : int {
   EPI_F32 = 4,         // out(f32) = acc + bias
   EPI_ATOMIC_F32 = 5,  // out(f32) += acc   (split-K wgrad, TMA reduce-add)
   EPI_PATCH_F32 = 6,   // out(f32)[b*T + extra + p] = acc + bias + pos[p]   (row = b*P + p), direct stores
+  EPI_DROP_RESID_F32 = 7,  // out(f32) = aux(f32) + dropout(acc + bias)   (mlp[2] + nn.Dropout + residual)
 };
 
 __host__ __device__ constexpr bool epi_out_is_f32(int kind) {
-  return kind == EPI_RESID_F32 || kind == EPI_F32 || kind == EPI_ATOMIC_F32 || kind == EPI_PATCH_F32;
+  return kind == EPI_RESID_F32 || kind == EPI_F32 || kind == EPI_ATOMIC_F32 || kind == EPI_PATCH_F32 ||
+         kind == EPI_DROP_RESID_F32;
 }
 
 struct EpiParams {
@@ -69,6 +72,8 @@ struct EpiParams {
   long long ldaux;
   const float* pos;  // [P, N] fp32
   int P, T, extra;
+  uint32_t drop_seed, drop_thr;  // EPI_DROP_RESID_F32: counter-based mask (dropout.cuh)
+  float drop_r;                  // 1 / (1 - p)
   float* colsum;     // wgrad only: colsum[m] += sum_k A(m, k)  (= bias gradient, summed from the smem A tiles)
 };
 
@@ -438,7 +443,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vbuf[c & 1][j]);
           if constexpr (KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_RESID_F32 || KIND == EPI_F32 ||
-                        KIND == EPI_PATCH_F32) {
+                        KIND == EPI_PATCH_F32 || KIND == EPI_DROP_RESID_F32) {
             if (ep.bias != nullptr) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -466,7 +471,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
             }
           } else if constexpr (OUT_F32) {
             // ---- fp32 output: one slab (32 rows x 32 cols) per chunk ----
-            if constexpr (KIND == EPI_RESID_F32) {
+            if constexpr (KIND == EPI_DROP_RESID_F32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const uint32_t h = drop_hash_rows(ep.drop_seed, (uint32_t)row, (uint32_t)((col + j) >> 1));
+                v[j] = drop_keep(h, 0, ep.drop_thr) ? v[j] * ep.drop_r : 0.f;
+                v[j + 1] = drop_keep(h, 1, ep.drop_thr) ? v[j + 1] * ep.drop_r : 0.f;
+              }
+            }
+            if constexpr (KIND == EPI_RESID_F32 || KIND == EPI_DROP_RESID_F32) {
               if (row_ok) {
                 const float* r = reinterpret_cast<const float*>(ep.aux) + (long long)row * ep.ldaux + col;
 #pragma unroll
