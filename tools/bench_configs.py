@@ -1,0 +1,98 @@
+"""Kernel / step timings for the other BASELINE.json configs (CUDA events), written as a markdown table.
+    python tools/bench_configs.py > profiles/rNN_other_configs.md
+configs[0] ViT-Ti 32px bs32, configs[2] TiTok-S 256px (encoder stack N=288 + VQ 4096x12), configs[3] ViT-L/16 224 bs256,
+configs[4] VideoGPT-B causal N=1024 (transformer stack only)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "vit-is-all-you-need_b200"))
+import torch  # noqa: E402
+
+from b200vit import modules as M  # noqa: E402
+from b200vit import ops  # noqa: E402
+
+dev = "cuda:0"
+peaks_hbm = 6525.2
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def layer_flops(N, d, causal=False):
+    att = 4 * N * N * d
+    return 2 * N * d * 3 * d + (att // 2 if causal else att) + 16 * N * d * d
+
+
+rows = []
+M.transformer_configs.setdefault("Ti", lambda **kw: M.TransformerConfig(12, 3, 192, **kw))
+
+
+def vit_step(name, size, patch, model, B, classes):
+    torch.manual_seed(0)
+    net = M.ViTClassifier(M.ViTConfig(size, 3, patch, model, 1, 0.0), num_classes=classes).to(dev)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, fused=True)
+    x = torch.randn(B, 3, size, size, device=dev)
+    y = torch.randint(0, classes, (B,), device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(net(x).float(), y)
+        loss.backward()
+        opt.step()
+    ms = timeit(step)
+    cfg = net.vit.transformer
+    N = (size // patch) ** 2 + 1
+    fl = 3 * cfg.n_layers * layer_flops(N, cfg.n_embd) * B
+    rows.append((name, f"{ms:.2f} ms/step", f"{B / ms * 1e3:.0f} img/s", f"{fl / ms / 1e9:.0f} TFLOP/s (transformer layers only)"))
+    del net, opt
+    torch.cuda.empty_cache()
+
+
+def stack_step(name, cfg, B, N, causal):
+    torch.manual_seed(0)
+    net = M.Transformer(cfg).to(dev)
+    x = torch.randn(B, N, cfg.n_embd, device=dev, requires_grad=True)
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        net(x).float().square().mean().backward()
+    ms = timeit(step)
+    fl = 3 * cfg.n_layers * layer_flops(N, cfg.n_embd, causal) * B
+    rows.append((name, f"{ms:.2f} ms fwd+bwd", f"{B / ms * 1e3:.0f} seq/s", f"{fl / ms / 1e9:.0f} TFLOP/s"))
+    del net
+    torch.cuda.empty_cache()
+
+
+vit_step("configs[0] ViT-Ti/4 32px, batch 32 (fwd+CE+bwd+AdamW)", 32, 4, "Ti", 32, 10)
+vit_step("configs[0] shape at batch 4096", 32, 4, "Ti", 4096, 10)
+vit_step("configs[3] ViT-L/16 224px, batch 256 (fwd+CE+bwd+AdamW)", 224, 16, "L", 256, 1000)
+stack_step("configs[2] TiTok-S encoder stack, N=288 (32 latent + 256 patches), batch 256", M.S(block_size=288), 256, 288, False)
+stack_step("configs[4] VideoGPT-B causal stack, N=1024, batch 16", M.B(block_size=1024, causal=True), 16, 1024, True)
+
+# VQ lookup: configs[2] (rows = B*32, K = 4096, D = 12) and the repo default (B*256 rows, K = 2048)
+for R, K in ((256 * 32, 4096), (256 * 256, 2048), (16 * 16 * 64, 1024)):
+    x = torch.randn(R, 12, device=dev)
+    cb = torch.randn(K, 12, device=dev)
+    ms = timeit(lambda: ops.vq_fwd(x, cb), iters=20)
+    flops = 2.0 * R * K * 12
+    bytes_ = R * 104 + K * 48
+    rows.append((f"VQ lookup fwd rows={R} K={K} D=12 (bit-exact indices)", f"{ms * 1e3:.1f} us", f"{flops / ms / 1e9:.2f} TFLOP/s fp32 FMA",
+                 f"{bytes_ / ms / 1e6:.1f} GB/s of {peaks_hbm:.0f} (104 B/row algorithmic; FMA-bound, see DESIGN.md)"))
+
+print("# Other BASELINE.json configs on one B200 (CUDA events, synthetic data; parity for these shapes is in tests/)\n")
+print("| case | time | rate | note |")
+print("|---|---:|---:|---|")
+for r in rows:
+    print("| " + " | ".join(r) + " |")

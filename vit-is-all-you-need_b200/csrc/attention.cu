@@ -1154,8 +1154,11 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
   const int w0 = ncols < 128 ? ncols : 128, w1 = ncols - w0;
   const Bwd2Layout L(ncols, nt);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar);
-  uint64_t* full = bars + 0;        // operands of the unit loaded
-  uint64_t* empty = bars + 1;       // operands consumed: dQ MMAs done and every warp's last store read its staging
+  // The operands are released one by one as the unit finishes with them, so the next unit's loads (there is no room
+  // for a second operand stage) overlap the tail of this one: Q / dO after the last dV / dK MMAs, K after the dQ
+  // MMAs, V once the dV read-out staged in its rows has been read by the TMA store.
+  uint64_t* full = bars + 13;       // [4] K, V, Q, dO loaded
+  uint64_t* empty = bars + 17;      // [3] K, V, Q+dO free
   uint64_t* sdp_full = bars + 2;    // [2] S^T, dP^T columns of query tile i complete
   uint64_t* pds_ready = bars + 4;   // [2] P^T, dS^T of query tile i written (4 warps)
   uint64_t* dkv_full = bars + 6;    // dV_j, dK_j complete
@@ -1164,7 +1167,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
   uint64_t* dq_free = bars + 9;     // dQ read out (4 nt warps)
   uint64_t* stats_full = bars + 10; // statistic vectors of the unit written (2 warps)
   uint64_t* stats_free = bars + 11; // statistic vectors no longer read (4 nt warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   float* nlse = reinterpret_cast<float*>(smem + L.vec);
   float* Dv = nlse + 256;
 
@@ -1174,7 +1177,8 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv_a); tma_prefetch_desc(&tm_qkv_b);
     tma_prefetch_desc(&tm_do_a); tma_prefetch_desc(&tm_do_b); tma_prefetch_desc(&tm_out);
-    mbar_init(full, 1); mbar_init(empty, 1 + 4 * nt);
+    for (int x = 0; x < 4; ++x) mbar_init(&full[x], 1);
+    mbar_init(&empty[0], 1); mbar_init(&empty[1], 1 + 4); mbar_init(&empty[2], 1);
     mbar_init(&sdp_full[0], 1); mbar_init(&sdp_full[1], 1);
     mbar_init(&pds_ready[0], 4); mbar_init(&pds_ready[1], 4);
     mbar_init(dkv_full, 1); mbar_init(dkv_free, 4 * nt);
@@ -1193,19 +1197,22 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
       int n = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
         const int b = u / p.H, hh = u - b * p.H;
-        mbar_wait(empty, (n & 1) ^ 1, 90);
-        mbar_expect_tx(full, 4 * L.OP);
-        // order: what the first S^T MMA needs (K, Q) first
-        tma_load_3d(smem + L.sK, &tm_qkv_a, full, p.d + hh * AT_HD, 0, b);
-        tma_load_3d(smem + L.sQ, &tm_qkv_a, full, hh * AT_HD, 0, b);
-        if (w1 > 0) tma_load_3d(smem + L.sQ + 16384, &tm_qkv_b, full, hh * AT_HD, 128, b);
-        tma_load_3d(smem + L.sV, &tm_qkv_a, full, 2 * p.d + hh * AT_HD, 0, b);
-        tma_load_3d(smem + L.sDO, &tm_do_a, full, hh * AT_HD, 0, b);
-        if (w1 > 0) {
-          tma_load_3d(smem + L.sDO + 16384, &tm_do_b, full, hh * AT_HD, 128, b);
-          tma_load_3d(smem + L.sK + 16384, &tm_qkv_b, full, p.d + hh * AT_HD, 128, b);
-          tma_load_3d(smem + L.sV + 16384, &tm_qkv_b, full, 2 * p.d + hh * AT_HD, 128, b);
-        }
+        const uint32_t ph = (n & 1) ^ 1;
+        mbar_wait(&empty[2], ph, 90);                      // Q, dO
+        mbar_expect_tx(&full[2], L.OP);
+        tma_load_3d(smem + L.sQ, &tm_qkv_a, &full[2], hh * AT_HD, 0, b);
+        if (w1 > 0) tma_load_3d(smem + L.sQ + 16384, &tm_qkv_b, &full[2], hh * AT_HD, 128, b);
+        mbar_expect_tx(&full[3], L.OP);
+        tma_load_3d(smem + L.sDO, &tm_do_a, &full[3], hh * AT_HD, 0, b);
+        if (w1 > 0) tma_load_3d(smem + L.sDO + 16384, &tm_do_b, &full[3], hh * AT_HD, 128, b);
+        mbar_wait(&empty[0], ph, 90);                      // K
+        mbar_expect_tx(&full[0], L.OP);
+        tma_load_3d(smem + L.sK, &tm_qkv_a, &full[0], p.d + hh * AT_HD, 0, b);
+        if (w1 > 0) tma_load_3d(smem + L.sK + 16384, &tm_qkv_b, &full[0], p.d + hh * AT_HD, 128, b);
+        mbar_wait(&empty[1], ph, 90);                      // V
+        mbar_expect_tx(&full[1], L.OP);
+        tma_load_3d(smem + L.sV, &tm_qkv_a, &full[1], 2 * p.d + hh * AT_HD, 0, b);
+        if (w1 > 0) tma_load_3d(smem + L.sV + 16384, &tm_qkv_b, &full[1], 2 * p.d + hh * AT_HD, 128, b);
         // there is no room for a second operand stage: pull the NEXT unit's tiles into L2 now, so that its loads
         // (issued when this unit releases the operands) are L2 hits
         const int u2 = u + gridDim.x;
@@ -1238,7 +1245,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
     const uint32_t idesc_s1 = umma_idesc_bf16(128, w1 > 0 ? w1 : 16, false, false);
     int n = 0, cc = 0;  // unit counter, chain (key tile) counter
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
-      mbar_wait(full, n & 1, 91);
+      for (int x = 0; x < 4; ++x) mbar_wait(&full[x], n & 1, 91);
       for (int j = 0; j < nt; ++j, ++cc) {
         // TMEM reuse: the previous chain's dV/dK (and, for the unit's first chain, the previous unit's dQ)
         // must have been read out before S^T / dP^T are overwritten
@@ -1278,7 +1285,10 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
           }
           __syncwarp();
         }
-        if (elected) umma_commit(dkv_full);
+        if (elected) {
+          umma_commit(dkv_full);
+          if (j == nt - 1) { umma_commit(&empty[2]); umma_commit(&empty[1]); }  // Q, dO (and V, MMA side) are done with
+        }
         __syncwarp();
       }
       // dQ_i = dS_i K over all keys; dS^T of both key tiles is in shared memory (pds_ready waited above)
@@ -1295,7 +1305,7 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
           a0 += 128; a1 += 128; bK += 128;
           acc = 1u;
         }
-        if (elected) { umma_commit(dq_full); umma_commit(empty); }
+        if (elected) { umma_commit(dq_full); umma_commit(&empty[0]); }   // K is done with
         __syncwarp();
       }
     }
@@ -1344,6 +1354,8 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
       int n = 0, cc = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++n) {
         const int b = u / p.H, hh = u - b * p.H;
+        if (lane == 0) bulk_wait_read();   // last unit's dQ store has left this warp's dS^T slab rows
+        __syncwarp();
         mbar_wait(stats_full, n & 1, 99);
         for (int j = 0; j < nt; ++j, ++cc) {
           const int key_local = j * 128 + r;            // row in the packed operands / dS^T slabs
@@ -1447,19 +1459,20 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
           __syncwarp();
           if (lane == 0) mbar_arrive(dkv_free);
         }
-        // ---- dQ of query tile i: lanes are query rows now; staged in V rows (tile 0) / dO rows (tile 1), both dead ----
+        // ---- dQ of query tile i: lanes are query rows now; staged in this warp's rows of dS^T slab 2i (dead: the
+        // dQ MMAs have completed), so no operand slot is held back from the next unit's loads ----
         mbar_wait(dq_full, n & 1, 97);
         tc_fence_after();
+        if (i == 0) {   // the dV_j store staged in the V rows has been read -> V may be refilled
+          if (lane == 0) { bulk_wait_read(); mbar_arrive(&empty[1]); }
+          __syncwarp();
+        }
         if (i * 128 + wq * 32 < ncols)
-          bwd2_store_tile(tmem_base + 128 + 64 * i + lane_off, p.scale, smem + (i == 0 ? L.sV : L.sDO) + wq * 4096,
+          bwd2_store_tile(tmem_base + 128 + 64 * i + lane_off, p.scale, smem + L.sDS + 2 * i * L.OP + wq * 4096,
                           i * 128 + r < ncols, &tm_out, hh * AT_HD, i * 128 + wq * 32, b, lane);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(dq_free);
-          bulk_wait_read();        // the staging rows inside the operand slots may now be overwritten by TMA loads
-          mbar_arrive(empty);
-        }
+        if (lane == 0) mbar_arrive(dq_free);
       }
       if (lane == 0) bulk_wait_all();
     }
