@@ -26,8 +26,10 @@ class _SinkLinear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w):
+        from b200vit import functional as Fn
         ctx.save_for_backward(x, w)
         ctx.w = w
+        ctx.sink = Fn._GRAD_SINK   # captured per autograd node, exactly like functional.TransformerStackFn
         return x @ w.t()
 
     @staticmethod
@@ -35,11 +37,11 @@ class _SinkLinear(torch.autograd.Function):
         from b200vit import functional as Fn
         x, w = ctx.saved_tensors
         gw = dy.t() @ x
-        slot = Fn._slot(ctx.w)
+        slot = Fn._slot(ctx.sink, ctx.w)
         if slot is not None:
             slot.copy_(gw)
-            gw = slot
-        Fn._ready(ctx.w)
+            gw = None   # delivered through the sink: autograd gets no second copy
+        Fn._ready(ctx.sink, ctx.w)
         return dy @ w, gw
 
 
@@ -80,8 +82,6 @@ def _worker(rank, world, port, tmpdir):
         ((ref(x) - y) ** 2).mean().backward()
         return [None if p.grad is None else p.grad.clone() for p in ref.parameters()], x, y
 
-    from b200vit import functional as Fn
-    Fn.set_grad_sink(None)
     per_rank = [local_grads(r) for r in range(world)]
     expect = []
     for i in range(len(w0)):
@@ -100,6 +100,9 @@ def _worker(rank, world, port, tmpdir):
             torch.testing.assert_close(p.grad, e, rtol=1e-5, atol=1e-6)
             slot = model.grad_slot(p)
             assert p.grad.data_ptr() == slot.data_ptr(), "param.grad must alias its bucket slot"
+        # an un-wrapped model trained in the same process (teacher, second network ...) is not routed into the sink
+        other, _, _ = local_grads(rank)
+        assert other[0] is not None
 
     # no_sync(): local gradients only
     for p in net.parameters():

@@ -28,9 +28,19 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--dropout", type=float, default=0.0)
 args = ap.parse_args()
 
-dev = torch.device("cuda:0")
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
 torch.manual_seed(0)
 model = M.ViTClassifier(M.ViTConfig(224, 3, 16, args.model, 1, args.dropout), num_classes=1000).to(dev)
+net = model
+if world > 1:  # torchrun: the same step through the data-parallel wrapper (rank 0 reports)
+    import torch.distributed as dist
+    from b200vit import ddp
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+    net = ddp.DataParallel(model)
 optim = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2, fused=True)
 x = torch.randn(args.batch, 3, 224, 224, device=dev)
 y = torch.randint(0, 1000, (args.batch,), device=dev)
@@ -39,7 +49,7 @@ y = torch.randint(0, 1000, (args.batch,), device=dev)
 def step():
     optim.zero_grad(set_to_none=True)
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        loss = torch.nn.functional.cross_entropy(model(x).float(), y)
+        loss = torch.nn.functional.cross_entropy(net(x).float(), y)
     loss.backward()
     optim.step()
     return loss
@@ -61,6 +71,9 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         step()
     torch.cuda.synchronize()
 
+if rank != 0:
+    dist.destroy_process_group()
+    sys.exit(0)
 evs = []
 for e in prof.events():
     if e.device_type == torch.autograd.DeviceType.CUDA:

@@ -79,11 +79,13 @@ class DataParallel(torch.nn.Module):
                 dist.broadcast(t.data, src=0, group=self.pg)
 
     def forward(self, *args, **kwargs):
-        if self._sync and torch.is_grad_enabled():
-            Fn.set_grad_sink(self)
-        else:
-            Fn.set_grad_sink(None)
-        return self.module(*args, **kwargs)
+        # the fused autograd nodes created during this forward capture the sink; other models in the process
+        # (a second wrapper, an un-wrapped teacher ...) are unaffected
+        prev = Fn.set_grad_sink(self if (self._sync and torch.is_grad_enabled()) else None)
+        try:
+            return self.module(*args, **kwargs)
+        finally:
+            Fn.set_grad_sink(prev)
 
     @contextlib.contextmanager
     def no_sync(self):
@@ -100,7 +102,8 @@ class DataParallel(torch.nn.Module):
         return None if s is None else s[1]
 
     def grad_ready(self, param):
-        self._mark_ready(param)
+        if param in self._slots:
+            self._mark_ready(param)
 
     def _hook(self, param):
         if not self._sync:

@@ -35,22 +35,24 @@ def bf16_of(p: torch.Tensor) -> torch.Tensor:
 # Gradient sink (set by ddp.DataParallel): lets the wgrad kernels write straight into all-reduce buckets and
 # start a bucket's all-reduce while the rest of the fused backward is still running.
 # ------------------------------------------------------------------------------------------------------------
-_GRAD_SINK = None
+_GRAD_SINK = None   # the sink of the DataParallel wrapper whose forward is running (captured per autograd node)
 
 
 def set_grad_sink(sink):
+    """Returns the previous sink so that the caller can restore it."""
     global _GRAD_SINK
-    _GRAD_SINK = sink
+    prev, _GRAD_SINK = _GRAD_SINK, sink
+    return prev
 
 
-def _slot(param):
-    return None if _GRAD_SINK is None else _GRAD_SINK.grad_slot(param)
+def _slot(sink, param):
+    return None if sink is None else sink.grad_slot(param)
 
 
-def _ready(*params):
-    if _GRAD_SINK is not None:
+def _ready(sink, *params):
+    if sink is not None:
         for p in params:
-            _GRAD_SINK.grad_ready(p)
+            sink.grad_ready(p)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -115,7 +117,7 @@ def layer_forward(x0, P: LayerParams, B, N, H, causal, save, dropout=(0.0, 0.0))
     return x2, saved
 
 
-def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_dx=True, dropout=(0.0, 0.0)):
+def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_dx=True, dropout=(0.0, 0.0), sink=None):
     """dx2: [B*N, d] fp32 (dx2_bf16: optional bf16 copy).  Returns (dx0, dx0_bf16, grads in LayerParams order)."""
     x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g, seeds = saved
     p_attn, p_mlp = dropout
@@ -123,21 +125,27 @@ def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_d
         dv = ops.dropout_cast_bf16(dx2, p_mlp, seeds[1])   # gradient through nn.Dropout, same mask as forward
     else:
         dv = dx2_bf16 if dx2_bf16 is not None else ops.cast_bf16(dx2)
-    d_fc2_w, d_fc2_b = ops.gemm_wgrad(dv, g, out=_slot(P.fc2_w), bias_out=_slot(P.fc2_b), want_bias=True)
-    _ready(P.fc2_w, P.fc2_b)
+    d_fc2_w, d_fc2_b = ops.gemm_wgrad(dv, g, out=_slot(sink, P.fc2_w), bias_out=_slot(sink, P.fc2_b), want_bias=True)
+    _ready(sink, P.fc2_w, P.fc2_b)
     du = ops.gemm_dgrad_dgelu(dv, bf16_of(P.fc2_w), u)
-    d_fc1_w, d_fc1_b = ops.gemm_wgrad(du, b, out=_slot(P.fc1_w), bias_out=_slot(P.fc1_b), want_bias=True)
-    _ready(P.fc1_w, P.fc1_b)
+    d_fc1_w, d_fc1_b = ops.gemm_wgrad(du, b, out=_slot(sink, P.fc1_w), bias_out=_slot(sink, P.fc1_b), want_bias=True)
+    _ready(sink, P.fc1_w, P.fc1_b)
     db = ops.gemm_dgrad(du, bf16_of(P.fc1_w))
     dx1, dx1_bf16, _, _ = ops.layernorm_bwd(db, x1, mean2, rstd2, dres=dx2, want_bf16=True)
     dqkv = ops.flash_attn_bwd(qkv, o, dx1_bf16.view(B, N, -1), lse, B, N, H, causal, dropout_p=p_attn, seed=seeds[0]).view(B * N, -1)
-    d_qkv_w, d_qkv_b = ops.gemm_wgrad(dqkv, a, out=_slot(P.qkv_w), bias_out=_slot(P.qkv_b), want_bias=True)
-    _ready(P.qkv_w, P.qkv_b)
+    d_qkv_w, d_qkv_b = ops.gemm_wgrad(dqkv, a, out=_slot(sink, P.qkv_w), bias_out=_slot(sink, P.qkv_b), want_bias=True)
+    _ready(sink, P.qkv_w, P.qkv_b)
     dx0 = dx0_bf16 = None
     if need_dx:
         da = ops.gemm_dgrad(dqkv, bf16_of(P.qkv_w))
         dx0, dx0_bf16, _, _ = ops.layernorm_bwd(da, x0, mean1, rstd1, dres=dx1, want_bf16=True)
-    return dx0, dx0_bf16, (d_qkv_w, d_qkv_b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b)
+    grads = (d_qkv_w, d_qkv_b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b)
+    if sink is not None:
+        # gradients already sit in their all-reduce bucket slots and have been marked ready: hand autograd None so
+        # that AccumulateGrad does not clone them into a second buffer (the sink points param.grad at the slots)
+        params = (P.qkv_w, P.qkv_b, P.fc1_w, P.fc1_b, P.fc2_w, P.fc2_b)
+        grads = tuple(None if _slot(sink, q) is not None else g_ for q, g_ in zip(params, grads))
+    return dx0, dx0_bf16, grads
 
 
 class TransformerStackFn(torch.autograd.Function):
@@ -160,6 +168,7 @@ class TransformerStackFn(torch.autograd.Function):
         ctx.saved_all = saved_all
         ctx.dims = (B, N, d, n_heads, causal)
         ctx.dropout = dropout
+        ctx.sink = _GRAD_SINK   # the data-parallel wrapper (if any) this forward ran under
         ctx.x_needs_grad = x.requires_grad
         return h.view(B, N, d)
 
@@ -172,7 +181,7 @@ class TransformerStackFn(torch.autograd.Function):
         n = len(ctx.layers)
         for i in range(n - 1, -1, -1):
             need_dx = i > 0 or ctx.x_needs_grad
-            dx, dx_bf16, g = layer_backward(dx, dx_bf16, ctx.saved_all[i], ctx.layers[i], B, N, H, causal, need_dx, ctx.dropout)
+            dx, dx_bf16, g = layer_backward(dx, dx_bf16, ctx.saved_all[i], ctx.layers[i], B, N, H, causal, need_dx, ctx.dropout, ctx.sink)
             ctx.saved_all[i] = None  # free activations as we go
             grads.append(g)
         flat = []
