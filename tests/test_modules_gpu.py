@@ -172,6 +172,35 @@ def test_residual_attention_block_matches_reference(golden_dir):
         check_grad(p.grad, g[f"g_{k}"], k)
 
 
+@pytest.mark.parametrize("C,d,p,H,W", [(3, 512, 16, 64, 64), (512, 768, 1, 32, 1), (3, 192, 8, 32, 64)])
+def test_patch_conv2d_matches_conv2d(C, d, p, H, W):
+    """PatchConv2d (what b200vit.launch installs as torch.nn.Conv2d): patchify-shaped convolutions -- the patch
+    embedding of blocks.TiTokEncoder (blocks.py:235-237,257) and the decoders' 1x1 convolutions -- against F.conv2d in
+    fp32 on the same bf16-rounded operands, forward and all gradients."""
+    from b200vit import modules as M
+    torch.manual_seed(C + d)
+    conv = M.PatchConv2d(C, d, kernel_size=p, stride=p).to(DEV)
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.bfloat16().float())
+    x = torch.randn(3, C, H, W, device=DEV).bfloat16().float().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = conv(x)
+    assert y.shape == (3, d, H // p, W // p)
+    ref = torch.nn.functional.conv2d(x, conv.weight, conv.bias, stride=p)
+    assert rel_l2(y.detach().cpu().numpy(), ref.detach().cpu().numpy()) < 1e-3
+    gy = torch.randn_like(ref).bfloat16().float()
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(ref, (x, conv.weight, conv.bias), gy)
+    gx, gw, gb = torch.autograd.grad(y, (x, conv.weight, conv.bias), gy)
+    check_grad(gx, gx_ref.cpu().numpy(), "PatchConv2d dx", tol=1e-2)
+    check_grad(gw, gw_ref.cpu().numpy(), "PatchConv2d dW", tol=1e-2)
+    check_grad(gb, gb_ref.cpu().numpy(), "PatchConv2d db", tol=1e-2)
+    # not patchify-shaped (or no autocast): plain nn.Conv2d behaviour
+    c3 = M.PatchConv2d(3, 8, kernel_size=3, padding=1).to(DEV)
+    xi = torch.randn(1, 3, 8, 8, device=DEV)
+    torch.testing.assert_close(c3(xi), torch.nn.functional.conv2d(xi, c3.weight, c3.bias, padding=1))
+    assert not conv._patchify_shaped(x.detach())  # autocast off
+
+
 def test_transformer_dropout_semantics():
     """dropout > 0 (train_vit.py default 0.15): train mode drops attention probabilities and the MLP output; eval
     mode keeps only SDPA's dropout_p (the reference passes it unconditionally, transformer.py:28); the expectation

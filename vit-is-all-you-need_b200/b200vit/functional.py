@@ -252,6 +252,36 @@ class PatchEmbedFn(torch.autograd.Function):
         return dx, dW, db, dpos, dextra, None
 
 
+class PatchConvFn(torch.autograd.Function):
+    """nn.Conv2d with kernel_size == stride (no padding / dilation / groups) as im2col + tcgen05 GEMM: the patch
+    embedding of blocks.TiTokEncoder (blocks.py:235-237,257) and the 1x1 convolutions of the tokenizer decoders
+    (blocks.py:329-333, train_titok.py:67).  Output is NCHW-shaped (a channels-last view of the GEMM result)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, p):
+        B, C, H, W = x.shape
+        d = weight.shape[0]
+        cols = ops.im2col_bf16(_as_rows_f32(x), p)
+        y = ops.gemm_bias_f32(cols, bf16_of(weight).view(d, -1), _f32c(bias))
+        ctx.saved = (cols, weight)
+        ctx.dims = (B, C, H, W, p, d)
+        ctx.x_needs_grad = x.requires_grad
+        ctx.has_bias = bias is not None
+        return y.view(B, H // p, W // p, d).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, weight = ctx.saved
+        B, C, H, W, p, d = ctx.dims
+        dy2 = dy.permute(0, 2, 3, 1).reshape(-1, d).to(BF16).contiguous()
+        dW, db = ops.gemm_wgrad(dy2, cols, want_bias=True)
+        dx = None
+        if ctx.x_needs_grad:
+            dcols = ops.gemm_dgrad(dy2, bf16_of(weight).view(d, -1))
+            dx = ops.col2im(dcols, B, C, H, W, p)
+        return dx, dW.view(weight.shape), (db if ctx.has_bias else None), None
+
+
 # ------------------------------------------------------------------------------------------------------------
 # blocks.ResidualAttentionBlock (blocks.py:32-70): affine LN, MHA (in_proj + out_proj), [L, B, d] layout
 # ------------------------------------------------------------------------------------------------------------

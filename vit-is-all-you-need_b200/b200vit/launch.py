@@ -8,6 +8,8 @@ What it does:
     `from train_vit import ViTConfig, ViT` and `import blocks` resolve to the sm_100a-backed classes;
   * classes the executed script defines itself (`ViT` in train_vit.py:30, `Quantizer` in train_titok.py:45 /
     train_vit_vqgan.py:45) are swapped at class-creation time through builtins.__build_class__;
+  * torch.nn.Conv2d becomes modules.PatchConv2d, a subclass that routes patchify-shaped convolutions (kernel == stride)
+    through the im2col + tcgen05 GEMM path and is otherwise nn.Conv2d;
   * stubs two imports the scripts never use (lpips, vector_quantize_pytorch.FSQ) when they are not installed,
     disables wandb, and (B200VIT_SYNTHETIC=1) replaces the hard-coded ImageNet loaders with synthetic ones.
 """
@@ -61,6 +63,19 @@ def install_class_swap(main_only=True):
     return orig
 
 
+def install_conv_swap():
+    """torch.nn.Conv2d -> PatchConv2d: patchify-shaped convolutions that the reference builds itself
+    (blocks.TiTokEncoder.patch_embed blocks.py:235, the decoders' 1x1 convolutions) take the im2col + tcgen05 GEMM path;
+    all other convolutions behave exactly as before (PatchConv2d falls through to nn.Conv2d)."""
+    import torch.nn as nn
+
+    from . import modules
+    orig = nn.Conv2d
+    nn.Conv2d = modules.PatchConv2d
+    nn.modules.conv.Conv2d = modules.PatchConv2d
+    return orig
+
+
 def install_synthetic_loaders():
     """datasets.get_imagenet_loaders has a hard-coded dataset root (datasets.py:7,23); benchmarks and smoke runs
     use synthetic tensors of the same shapes instead."""
@@ -95,6 +110,7 @@ def main(argv=None):
     if os.environ.get("B200VIT_SYNTHETIC", "0") == "1":
         install_synthetic_loaders()
     orig = install_class_swap()
+    install_conv_swap()
     sys.argv = [script] + argv[1:]
     try:
         runpy.run_path(script, run_name="__main__")

@@ -167,6 +167,26 @@ class ViTClassifier(nn.Module):
         return self.head(self.vit(x)[:, 0])
 
 
+class PatchConv2d(nn.Conv2d):
+    """nn.Conv2d whose patchify-shaped instances (kernel_size == stride, no padding / dilation / groups: the patch
+    embedding of blocks.TiTokEncoder blocks.py:235-237, the 1x1 convolutions of the decoders blocks.py:329-333 /
+    train_titok.py:67) run as im2col + tcgen05 GEMM on CUDA under autocast; every other use falls through to
+    nn.Conv2d unchanged.  Same parameters and state_dict keys.  b200vit.launch installs it as torch.nn.Conv2d."""
+
+    def _patchify_shaped(self, x):
+        k, s = self.kernel_size, self.stride
+        return (x.is_cuda and x.dim() == 4 and torch.is_autocast_enabled() and k[0] == k[1] == s[0] == s[1]
+                and self.padding == (0, 0) and self.dilation == (1, 1) and self.groups == 1
+                and self.padding_mode == "zeros" and x.shape[2] % k[0] == 0 and x.shape[3] % k[0] == 0
+                and (self.in_channels * k[0] * k[0]) % 8 == 0 and self.out_channels % 8 == 0
+                and (k[0] == 1 or x.shape[3] % 4 == 0))
+
+    def forward(self, x):
+        if self._patchify_shaped(x):
+            return Fn.PatchConvFn.apply(x, self.weight, self.bias, self.kernel_size[0])
+        return super().forward(x)
+
+
 # ------------------------------------------------------------------------------------------------ train_titok.py
 class Quantizer(nn.Module):
     """train_titok.Quantizer (train_titok.py:45-59 == train_vit_vqgan.py:45-59): indices from l2-normalised

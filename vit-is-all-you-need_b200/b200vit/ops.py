@@ -266,6 +266,14 @@ def patch_embed_bwd_reduce(dtokens, extra):
     return dsum, dpe
 
 
+def im2col_bf16(x, p):
+    """x [B, C, H, W] fp32 -> bf16 patch rows [B * (H/p) * (W/p), C * p * p] in (c, i, j) order (the conv weight's)."""
+    B, C, H, W = x.shape
+    cols = torch.empty(B * (H // p) * (W // p), C * p * p, device=x.device, dtype=BF16)
+    _call("b200vit_im2col_bf16", x, ptr(_chk(x, F32, "x")), ptr(cols), B, C, H, W, p, stream_ptr())
+    return cols
+
+
 def col2im(dcols, B, C, H, W, p):
     dx = torch.empty(B, C, H, W, device=dcols.device, dtype=F32)
     _call("b200vit_col2im_f32", dcols, ptr(_chk(dcols, BF16, "dcols")), ptr(dx), B, C, H, W, p, stream_ptr())

@@ -1,2 +1,24 @@
-"""Drop-in for the hot-path classes of the reference's `blocks` module (blocks.py:32-70, 405-505)."""
-from b200vit.modules import ResidualAttentionBlock, VectorQuantizer  # noqa: F401
+"""Drop-in for the reference's top-level module `blocks`.
+
+The hot-path classes (ResidualAttentionBlock blocks.py:32-70, VectorQuantizer blocks.py:405-505) come from
+b200vit.modules; everything else the reference's blocks.py defines (TiTokEncoder / TiTokDecoder blocks.py:208-361,
+UViTBlock, ...) is taken from the reference's own file, executed in this module's namespace, so that
+`from blocks import TiTokEncoder, TiTokDecoder, VectorQuantizer` (train_tatitok.py:13) keeps working and the encoder /
+decoder assemble themselves out of the sm_100a-backed blocks (they look `ResidualAttentionBlock` up by its module-global
+name when they are constructed)."""
+import os
+import sys
+
+from b200vit.modules import ResidualAttentionBlock as _RAB
+from b200vit.modules import VectorQuantizer as _VQ
+
+_here = os.path.dirname(os.path.abspath(__file__))
+for _p in sys.path:
+    _cand = os.path.join(_p or ".", "blocks.py")
+    if os.path.isfile(_cand) and os.path.abspath(os.path.dirname(_cand)) != _here:
+        with open(_cand) as _f:
+            exec(compile(_f.read(), _cand, "exec"), globals())  # the reference's own definitions, unmodified
+        break
+
+ResidualAttentionBlock = _RAB
+VectorQuantizer = _VQ
