@@ -105,6 +105,11 @@ def ensure_device(device_index: int):
         rc = lib.b200vit_init(c_int(device_index))
         if rc != 0:
             raise B200VitError(lib.b200vit_last_error().decode())
+        # bring-up knobs for A/B measurements, e.g. B200VIT_DEBUG="10=1" (programmatic dependent launch off)
+        for kv in os.environ.get("B200VIT_DEBUG", "").split(","):
+            if "=" in kv:
+                k, v = kv.split("=")
+                lib.b200vit_debug_set(int(k), int(v))
         _inited_devices.add(device_index)
     return lib
 

@@ -427,6 +427,8 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // the set-up above overlapped the previous kernel's tail
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1191,6 +1193,8 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // the set-up above overlapped the previous kernel's tail
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1543,8 +1547,8 @@ int b200vit_flash_attn_fwd_dropout(const void* qkv, void* o, float* lse, int B, 
     if (rc != OK) return rc;
     const int units = B * H;
     const int g = units < num_sms() ? units : num_sms();
-    if (p.drop_thr != 0) attn_fwd_short_kernel<true><<<g, AS_THREADS, FwdShortSmem::TOTAL, st>>>(tm, tm_o, p);
-    else                 attn_fwd_short_kernel<false><<<g, AS_THREADS, FwdShortSmem::TOTAL, st>>>(tm, tm_o, p);
+    if (p.drop_thr != 0) launch_kernel(attn_fwd_short_kernel<true>, dim3(g), dim3(AS_THREADS), FwdShortSmem::TOTAL, st, 1, tm, tm_o, p);
+    else                 launch_kernel(attn_fwd_short_kernel<false>, dim3(g), dim3(AS_THREADS), FwdShortSmem::TOTAL, st, 1, tm, tm_o, p);
     B200_CUDA(cudaGetLastError());
     return OK;
   }
@@ -1615,8 +1619,8 @@ int b200vit_flash_attn_bwd_dropout(const void* qkv, const void* o, const void* d
     B200_CUDA(cudaFuncSetAttribute(attn_bwd_short_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.alloc_bytes(nt)));
     const int units = B * H;
     const int g = units < num_sms() ? units : num_sms();
-    if (p.drop_thr != 0) attn_bwd_short_kernel<true><<<g, AB2_THREADS, L.alloc_bytes(nt), st>>>(qa, qb, da, db, tout, p);
-    else                 attn_bwd_short_kernel<false><<<g, AB2_THREADS, L.alloc_bytes(nt), st>>>(qa, qb, da, db, tout, p);
+    if (p.drop_thr != 0) launch_kernel(attn_bwd_short_kernel<true>, dim3(g), dim3(AB2_THREADS), (size_t)L.alloc_bytes(nt), st, 1, qa, qb, da, db, tout, p);
+    else                 launch_kernel(attn_bwd_short_kernel<false>, dim3(g), dim3(AB2_THREADS), (size_t)L.alloc_bytes(nt), st, 1, qa, qb, da, db, tout, p);
     B200_CUDA(cudaGetLastError());
     return OK;
   }

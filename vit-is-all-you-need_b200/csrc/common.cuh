@@ -248,6 +248,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn, 
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// ---- programmatic dependent launch (PDL) ----
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization may start their prologue (barrier init,
+// TMEM allocation, descriptor prefetch) while the previous kernel in the stream drains.  pdl_wait() blocks until
+// every prerequisite grid has completed and its memory is visible: it must precede the first global access.
+// pdl_trigger() lets the NEXT kernel do the same once all CTAs of this grid have passed it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- small math helpers ----
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -278,6 +286,39 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 #endif  // __CUDACC__
+
+// ----------------------------------------------------------------------------------------------
+// Host: kernel launch with optional cluster dimension and programmatic dependent launch
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  // Programmatic dependent launch is OFF by default: an A/B on one box (bench.py, B200VIT_DEBUG="10=1") showed no
+  // gain (29.4 / 29.5 ms with, 29.0 / 29.5 ms without) -- the step runs under the 1 kW power cap, so removing the
+  // ~2 us gaps between kernels only lowers the clocks.  Knob 10 = 1 switches it on.
+  if (g_debug[10] == 1) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // Host: TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency)

@@ -69,17 +69,7 @@ static int launch(const void* A, long long lda, const void* B, long long ldb, in
     attr_done = true;
   }
   const int nwork = s.total_work < workers ? s.total_work : workers;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(nwork * NCTA);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, to2, s, ep));
+  B200_CUDA(launch_kernel(kern, dim3(nwork * NCTA), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, st, NCTA, ta, tb, to, to2, s, ep));
   return OK;
 }
 

@@ -246,6 +246,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if constexpr (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------

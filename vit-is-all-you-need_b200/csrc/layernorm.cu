@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(LNF_THREADS) ln_fwd_fast_kernel(const LnFwdArg
   constexpr int D = CH * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * LNF_WARPS + warp;
+  pdl_wait();
+  pdl_trigger();
   if (row >= a.M) return;
   const float* xr = a.x + row * D + lane * 4;
   float4 v[CH];
@@ -268,6 +270,8 @@ __global__ void __launch_bounds__(LNF_THREADS) ln_bwd_fast_kernel(const LnBwdArg
   constexpr int D = CH * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * LNF_WARPS + warp;
+  pdl_wait();
+  pdl_trigger();
   if (row >= a.M) return;
   const float mean = __ldg(a.mean + row), rstd = __ldg(a.rstd + row);
   const float* xr = a.x + row * D + lane * 4;
@@ -326,11 +330,11 @@ static bool launch_ln_fwd_fast(const LnFwdArgs& a, cudaStream_t st) {
   const int grid = (a.M + LNF_WARPS - 1) / LNF_WARPS;
   const bool affine = a.gamma != nullptr && a.beta != nullptr;
   if (a.add != nullptr) {
-    if (affine) ln_fwd_fast_kernel<CH, true, true><<<grid, LNF_THREADS, 0, st>>>(a);
-    else        ln_fwd_fast_kernel<CH, true, false><<<grid, LNF_THREADS, 0, st>>>(a);
+    if (affine) launch_kernel(ln_fwd_fast_kernel<CH, true, true>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
+    else        launch_kernel(ln_fwd_fast_kernel<CH, true, false>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
   } else {
-    if (affine) ln_fwd_fast_kernel<CH, false, true><<<grid, LNF_THREADS, 0, st>>>(a);
-    else        ln_fwd_fast_kernel<CH, false, false><<<grid, LNF_THREADS, 0, st>>>(a);
+    if (affine) launch_kernel(ln_fwd_fast_kernel<CH, false, true>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
+    else        launch_kernel(ln_fwd_fast_kernel<CH, false, false>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
   }
   return true;
 }
@@ -348,8 +352,8 @@ static bool try_ln_fwd_fast(const LnFwdArgs& a, cudaStream_t st) {
 template <int CH>
 static bool launch_ln_bwd_fast(const LnBwdArgs& a, cudaStream_t st) {
   const int grid = (a.M + LNF_WARPS - 1) / LNF_WARPS;
-  if (a.gamma != nullptr) ln_bwd_fast_kernel<CH, true><<<grid, LNF_THREADS, 0, st>>>(a);
-  else                    ln_bwd_fast_kernel<CH, false><<<grid, LNF_THREADS, 0, st>>>(a);
+  if (a.gamma != nullptr) launch_kernel(ln_bwd_fast_kernel<CH, true>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
+  else                    launch_kernel(ln_bwd_fast_kernel<CH, false>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
   return true;
 }
 static bool try_ln_bwd_fast(const LnBwdArgs& a, cudaStream_t st) {
