@@ -12,6 +12,7 @@ dev = "cuda:0"
 B, N, H = int(os.environ.get("B", 256)), int(os.environ.get("N", 197)), int(os.environ.get("H", 12))
 d = H * 64
 iters = int(os.environ.get("ITERS", 5))
+causal = os.environ.get("CAUSAL", "0") == "1"
 
 
 def timeit(fn, iters=iters, warm=2):
@@ -29,12 +30,14 @@ def timeit(fn, iters=iters, warm=2):
 
 qkv = torch.randn(B, N, 3 * d, device=dev).to(torch.bfloat16)
 do = torch.randn(B, N, d, device=dev).to(torch.bfloat16)
-o, lse = ops.flash_attn_fwd(qkv, B, N, H, False)
-fl = 4.0 * N * N * d * B
-t = timeit(lambda: ops.flash_attn_fwd(qkv, B, N, H, False))
-print(f"attn fwd  B={B} N={N} H={H}: {t:8.1f} us  {fl/t/1e6:7.1f} TFLOP/s (algorithmic 4*N^2*d*B)")
-t = timeit(lambda: ops.flash_attn_bwd(qkv, o, do, lse, B, N, H, False))
+o, lse = ops.flash_attn_fwd(qkv, B, N, H, causal)
+fl = 4.0 * N * N * d * B * (0.5 if causal else 1.0)
+t = timeit(lambda: ops.flash_attn_fwd(qkv, B, N, H, causal))
+print(f"attn fwd  B={B} N={N} H={H} causal={causal}: {t:8.1f} us  {fl/t/1e6:7.1f} TFLOP/s (algorithmic 4*N^2*d*B)")
+t = timeit(lambda: ops.flash_attn_bwd(qkv, o, do, lse, B, N, H, causal))
 print(f"attn bwd  B={B} N={N} H={H}: {t:8.1f} us  {2.5*fl/t/1e6:7.1f} TFLOP/s (2.5x fwd)")
+if "--attn-only" in sys.argv:
+    sys.exit(0)
 if "--sdpa" in sys.argv:
     q, k, v = (qkv.view(B, N, 3, H, 64)[:, :, i].transpose(1, 2) for i in range(3))
     t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))

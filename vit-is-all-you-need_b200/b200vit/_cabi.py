@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200vit.so")
+LIB_PATH = os.environ.get("B200VIT_LIB") or os.path.join(_HERE, "libb200vit.so")  # B200VIT_LIB: experiment builds
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), "include", "b200vit.h")
 
 _lib = None

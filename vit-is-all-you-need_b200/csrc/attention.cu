@@ -157,31 +157,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, AT_HD, false, true);
-      const uint32_t sQ = smem_u32(smem + FwdSmem::Q);
-      const uint32_t sP = smem_u32(smem + FwdSmem::P);
-      mbar_wait(q_full, 0, 20);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        const uint32_t sK = smem_u32(smem + FwdSmem::KV + st * 2 * AT_TILE_BYTES);
-        const uint32_t sV = sK + AT_TILE_BYTES;
-        const int nkeys = min(AT_BK, p.N - j * AT_BK);     // valid keys of this block
-        const int ncols = ((nkeys + 31) >> 5) << 5;        // S columns the softmax warps will read
-        const uint32_t idesc_s = umma_idesc_bf16(128, ncols, false, false);
-        mbar_wait(&kv_full[st], (j >> 1) & 1, 21);
-        tc_fence_after();
+    // warp-uniform control flow, one elected lane issues (descriptors stay in uniform registers; see the short kernels)
+    const bool elected = elect_one();
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, AT_HD, false, true);
+    const uint32_t sQ = smem_u32(smem + FwdSmem::Q);
+    const uint32_t sP = smem_u32(smem + FwdSmem::P);
+    mbar_wait(q_full, 0, 20);
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j & 1;
+      const uint32_t sK = smem_u32(smem + FwdSmem::KV + st * 2 * AT_TILE_BYTES);
+      const uint32_t sV = sK + AT_TILE_BYTES;
+      const int nkeys = min(AT_BK, p.N - j * AT_BK);     // valid keys of this block
+      const int ncols = ((nkeys + 31) >> 5) << 5;        // S columns the softmax warps will read
+      const uint32_t idesc_s = umma_idesc_bf16(128, ncols, false, false);
+      const uint64_t dQ = desc_kmajor(sQ, 0), dK = desc_kmajor(sK, 0);
+      mbar_wait(&kv_full[st], (j >> 1) & 1, 21);
+      tc_fence_after();
+      if (elected) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, dQ + 2 * k, dK + 2 * k, idesc_s, k > 0);
         umma_commit(s_full);
-        mbar_wait(p_ready, j & 1, 22);
-        tc_fence_after();
-        const int ksteps = (nkeys + 15) >> 4;              // P columns beyond the valid keys are zero / unused
-        for (int k = 0; k < ksteps; ++k)
-          umma_bf16(tmem_O, desc_kmajor(sP + (k >> 2) * AT_TILE_BYTES, k & 3), desc_mnmajor(sV, k, 8192), idesc_o, k > 0);
-        umma_commit(o_full);
-        umma_commit(&kv_empty[st]);
       }
+      __syncwarp();
+      mbar_wait(p_ready, j & 1, 22);
+      tc_fence_after();
+      const int ksteps = (nkeys + 15) >> 4;              // P columns beyond the valid keys are zero / unused
+      uint64_t dV = desc_mnmajor(sV, 0, 8192);
+      uint32_t acc = 0u;
+#pragma unroll 2
+      for (int k = 0; k < ksteps; ++k) {
+        const uint64_t dP = desc_kmajor(sP + (k >> 2) * AT_TILE_BYTES, k & 3);
+        if (elected) umma_bf16(tmem_O, dP, dV, idesc_o, acc);
+        dV += 128; acc = 1u;
+      }
+      if (elected) { umma_commit(o_full); umma_commit(&kv_empty[st]); }
+      __syncwarp();
     }
   } else {
     // ---- softmax warps: thread <-> query row ----
@@ -726,43 +736,52 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, AT_BK, false, false);   // S, dP: K-major x K-major
-      constexpr uint32_t idesc_t = umma_idesc_bf16(128, AT_HD, true, true);     // dV, dK: MN-major x MN-major
-      constexpr uint32_t idesc_q = umma_idesc_bf16(128, AT_HD, false, true);    // dQ: K-major x MN-major
-      const uint32_t sK = smem_u32(smem + BwdSmem::K), sV = smem_u32(smem + BwdSmem::V);
-      const uint32_t sP = smem_u32(smem + BwdSmem::P), sDS = smem_u32(smem + BwdSmem::DS);
-      mbar_wait(kv_full, 0, 50);
-      for (int it = 0; it < ntiles; ++it) {
-        const int st = it & 1;
-        const uint32_t sQ = smem_u32(smem + BwdSmem::QDO + st * 2 * AT_TILE_BYTES);
-        const uint32_t sDO = sQ + AT_TILE_BYTES;
-        mbar_wait(&q_full[st], (it >> 1) & 1, 51);
-        tc_fence_after();
+    const bool elected = elect_one();   // warp-uniform control flow, one elected lane issues
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, AT_BK, false, false);   // S, dP: K-major x K-major
+    constexpr uint32_t idesc_t = umma_idesc_bf16(128, AT_HD, true, true);     // dV, dK: MN-major x MN-major
+    constexpr uint32_t idesc_q = umma_idesc_bf16(128, AT_HD, false, true);    // dQ: K-major x MN-major
+    const uint32_t sK = smem_u32(smem + BwdSmem::K), sV = smem_u32(smem + BwdSmem::V);
+    const uint32_t sP = smem_u32(smem + BwdSmem::P), sDS = smem_u32(smem + BwdSmem::DS);
+    mbar_wait(kv_full, 0, 50);
+    for (int it = 0; it < ntiles; ++it) {
+      const int st = it & 1;
+      const uint32_t sQ = smem_u32(smem + BwdSmem::QDO + st * 2 * AT_TILE_BYTES);
+      const uint32_t sDO = sQ + AT_TILE_BYTES;
+      mbar_wait(&q_full[st], (it >> 1) & 1, 51);
+      tc_fence_after();
+      if (elected) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_S, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_dP, desc_kmajor(sDO, k), desc_kmajor(sV, k), idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k) {   // independent accumulators interleaved
+          umma_bf16(tmem_S, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_s, k > 0);
+          umma_bf16(tmem_dP, desc_kmajor(sDO, k), desc_kmajor(sV, k), idesc_s, k > 0);
+        }
         umma_commit(sdp_full);
-        mbar_wait(pds_ready, it & 1, 52);
-        tc_fence_after();
-        // dV[key, d] += P^T dO ; dK[key, d] += dS^T Q   (contraction over the 128 query rows)
+      }
+      __syncwarp();
+      mbar_wait(pds_ready, it & 1, 52);
+      tc_fence_after();
+      // dV[key, d] += P^T dO ; dK[key, d] += dS^T Q   (contraction over the 128 query rows)
+      if (elected) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 8; ++k) {
           umma_bf16(tmem_dV, desc_mnmajor(sP, k, 16384), desc_mnmajor(sDO, k, 8192), idesc_t, (it > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
           umma_bf16(tmem_dK, desc_mnmajor(sDS, k, 16384), desc_mnmajor(sQ, k, 8192), idesc_t, (it > 0 || k > 0) ? 1u : 0u);
-        if (it > 0) { mbar_wait(dq_free, (it - 1) & 1, 53); tc_fence_after(); }
-        // dQ[q, d] = dS K   (contraction over the 128 keys)
+        }
+      }
+      __syncwarp();
+      if (it > 0) { mbar_wait(dq_free, (it - 1) & 1, 53); tc_fence_after(); }
+      // dQ[q, d] = dS K   (contraction over the 128 keys)
+      if (elected) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_bf16(tmem_dQ, desc_kmajor(sDS + (k >> 2) * AT_TILE_BYTES, k & 3), desc_mnmajor(sK, k, 8192), idesc_q, k > 0);
         umma_commit(dq_full);
         umma_commit(&q_empty[st]);
       }
-      umma_commit(dkv_full);
+      __syncwarp();
     }
+    if (elected) umma_commit(dkv_full);
+    __syncwarp();
   } else {
     const int r = threadIdx.x;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
