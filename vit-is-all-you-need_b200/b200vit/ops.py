@@ -24,41 +24,52 @@ _KERNELS_PER_CALL = {"b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3}
 _prof = None  # list of (start_event, end_event, flops) while profile_gemms() is active
 
 
-def _call(name, t, *args, flops=None):
+def _call(name, t, *args, flops=None, hbm_bytes=None):
     global launch_count
     lib = _cabi.lib_for(t)  # raises for CPU tensors / missing library / non-sm_100 devices
     launch_count += _KERNELS_PER_CALL.get(name, 1)
     args = tuple(_cabi.stream_ptr() if a is _STREAM else a for a in args)
-    if _prof is not None and flops is not None:
+    work = flops if flops is not None else hbm_bytes
+    if _prof is not None and work is not None and (flops is not None) == (_prof_kind == "flops"):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _cabi.check(getattr(lib, name)(*args))
         e1.record()
-        _prof.append((e0, e1, flops, name))
+        _prof.append((e0, e1, work, name))
         return
     _cabi.check(getattr(lib, name)(*args))
 
 
-def profile_gemms(fn, steps=1):
-    """Runs fn() `steps` times with a CUDA-event pair around every tcgen05 GEMM launch (on the launching stream).
-    Returns (total GEMM milliseconds, total algorithmic FLOPs, number of launches)."""
-    global _prof
-    _prof = []
+_prof_kind = "flops"
+
+
+def profile_kernels(fn, steps=1, kind="flops"):
+    """Runs fn() `steps` times with a CUDA-event pair (on the launching stream) around every C-ABI launch that
+    declares its algorithmic work: kind="flops" -> the tcgen05 GEMMs (2MNK), kind="bytes" -> the HBM-bound kernels
+    (LayerNorm: algorithmic bytes).  Returns (total ms, total work, launches, per-entry-point detail)."""
+    global _prof, _prof_kind
+    _prof, _prof_kind = [], kind
     try:
         for _ in range(steps):
             fn()
         torch.cuda.synchronize()
         ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in _prof)
-        fl = float(sum(f for _, _, f, _ in _prof))
+        work = float(sum(f for _, _, f, _ in _prof))
         n = len(_prof)
         detail = {}
         for e0, e1, f, name in _prof:
             d = detail.setdefault(name, [0.0, 0.0, 0])
             d[0] += e0.elapsed_time(e1); d[1] += f; d[2] += 1
-        profile_gemms.last_detail = {k: {"ms": v[0], "tflops": v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 else 0.0, "launches": v[2]}
-                                     for k, v in detail.items()}
+        detail = {k: {"ms": v[0], "rate": v[1] / (v[0] / 1e3) if v[0] > 0 else 0.0, "launches": v[2]} for k, v in detail.items()}
     finally:
-        _prof = None
+        _prof, _prof_kind = None, "flops"
+    return ms, work, n, detail
+
+
+def profile_gemms(fn, steps=1):
+    """(total GEMM milliseconds, total algorithmic FLOPs, number of launches) -- see profile_kernels."""
+    ms, fl, n, detail = profile_kernels(fn, steps, "flops")
+    profile_gemms.last_detail = {k: {"ms": v["ms"], "tflops": v["rate"] / 1e12, "launches": v["launches"]} for k, v in detail.items()}
     return ms, fl, n
 
 
@@ -202,7 +213,9 @@ def layernorm_fwd(x, add=None, gamma=None, beta=None, want_x_out=False, out_bf16
     mean = torch.empty(M, device=x.device, dtype=F32)
     rstd = torch.empty(M, device=x.device, dtype=F32)
     x_out = torch.empty_like(x) if want_x_out else None
-    _call("b200vit_layernorm_fwd", x, ptr(_chk(x, F32, "x")), ptr(add), ptr(x_out), ptr(gamma), ptr(beta), ptr(y), ptr(y32), ptr(mean), ptr(rstd), M, d, eps, stream_ptr())
+    nbytes = M * d * (4 + (2 if add is not None else 0) + (4 if want_x_out else 0) + (2 if out_bf16 else 0) + (4 if out_f32 else 0)) + 8 * M
+    _call("b200vit_layernorm_fwd", x, ptr(_chk(x, F32, "x")), ptr(add), ptr(x_out), ptr(gamma), ptr(beta), ptr(y), ptr(y32), ptr(mean), ptr(rstd), M, d, eps, stream_ptr(),
+          hbm_bytes=float(nbytes))
     return y, y32, mean, rstd, x_out
 
 
@@ -215,7 +228,9 @@ def layernorm_bwd(dy, x, mean, rstd, gamma=None, dres=None, want_bf16=True, affi
     db = torch.empty(d, device=x.device, dtype=F32) if affine_grads else None
     dy16 = dy if dy.dtype == BF16 else None
     dy32 = dy if dy.dtype == F32 else None
-    _call("b200vit_layernorm_bwd", x, ptr(dy16), ptr(dy32), ptr(_chk(x, F32, "x")), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx), ptr(dxb), ptr(dg), ptr(db), M, d, stream_ptr())
+    nbytes = M * d * ((2 if dy16 is not None else 4) + 4 + (4 if dres is not None else 0) + 4 + (2 if want_bf16 else 0)) + 8 * M
+    _call("b200vit_layernorm_bwd", x, ptr(dy16), ptr(dy32), ptr(_chk(x, F32, "x")), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx), ptr(dxb), ptr(dg), ptr(db), M, d, stream_ptr(),
+          hbm_bytes=float(nbytes))
     return dx, dxb, dg, db
 
 
