@@ -71,6 +71,7 @@ int b200vit_gemm_wgrad_bias(const void* dy, const void* x, float* dw, float* db,
  * seq_first != 0: tensors are [N, B, ...] (the LND layout of blocks.py:270) instead of [B, N, ...]. */
 int b200vit_flash_attn_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int causal, int seq_first,
                            void* stream);
+/* bytes of fp32 workspace the backward needs (0 for N <= 256: the resident kernels accumulate in TMEM only)        */
 size_t b200vit_flash_attn_bwd_workspace_size(int B, int N, int H);
 /* dqkv: [B, N, 3, H, 64] bf16 gradient of qkv given d_o [B, N, H*64] bf16 */
 int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B,

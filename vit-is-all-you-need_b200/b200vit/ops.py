@@ -197,7 +197,8 @@ def flash_attn_fwd(qkv, B, N, H, causal=False, want_lse=True, seq_first=False, d
 def flash_attn_bwd(qkv, o, d_o, lse, B, N, H, causal=False, seq_first=False, dropout_p=0.0, seed=0):
     d = H * 64
     dqkv = torch.empty((N, B, 3 * d) if seq_first else (B, N, 3 * d), device=qkv.device, dtype=BF16)
-    ws = torch.empty(B * N * d, device=qkv.device, dtype=F32)
+    ws_bytes = _cabi.lib_for(qkv).b200vit_flash_attn_bwd_workspace_size(B, N, H)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=qkv.device, dtype=F32)
     _call("b200vit_flash_attn_bwd_dropout", qkv, ptr(_chk(qkv, BF16, "qkv")), ptr(_chk(o, BF16, "o")), ptr(_chk(d_o, BF16, "d_o")), ptr(_chk(lse, F32, "lse")),
           ptr(dqkv), B, N, H, 1 if causal else 0, 1 if seq_first else 0, float(dropout_p), int(seed) & 0xFFFFFFFF,
           ptr(ws), ws.numel() * 4, stream_ptr())

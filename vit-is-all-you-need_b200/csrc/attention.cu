@@ -1583,7 +1583,7 @@ int b200vit_flash_attn_fwd_dropout(const void* qkv, void* o, float* lse, int B, 
 }
 
 size_t b200vit_flash_attn_bwd_workspace_size(int B, int N, int H) {
-  return (size_t)B * N * H * AT_HD * sizeof(float);
+  return N > 256 ? (size_t)B * N * H * AT_HD * sizeof(float) : 0;   // resident kernels (N <= 256): no workspace
 }
 
 int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
@@ -1596,9 +1596,12 @@ int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, cons
 int b200vit_flash_attn_bwd_dropout(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
                                    int B, int N, int H, int causal, int seq_first, float dropout_p,
                                    unsigned int seed, void* workspace, size_t workspace_bytes, void* stream) {
-  B200_REQUIRE(qkv && o && d_o && lse && dqkv && workspace, "flash_attn_bwd: null pointer");
+  B200_REQUIRE(qkv && o && d_o && lse && dqkv, "flash_attn_bwd: null pointer");
   B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "flash_attn_bwd: dropout_p must be in [0, 1)");
-  B200_REQUIRE(workspace_bytes >= b200vit_flash_attn_bwd_workspace_size(B, N, H), "flash_attn_bwd: workspace too small");
+  // only the streaming kernel (N > 256) accumulates dQ through an fp32 workspace; the resident kernels need none
+  const bool needs_ws = N > 256;
+  B200_REQUIRE(!needs_ws || (workspace && workspace_bytes >= b200vit_flash_attn_bwd_workspace_size(B, N, H)),
+               "flash_attn_bwd: workspace missing or too small");
   const int d = H * AT_HD;
   CUtensorMap tm_qkv, tm_do;
   int rc = make_tmap_bnd(&tm_qkv, qkv, B, N, 3 * d, seq_first);
@@ -1643,7 +1646,7 @@ int b200vit_flash_attn_bwd_dropout(const void* qkv, const void* o, const void* d
     B200_CUDA(cudaGetLastError());
     return OK;
   }
-  if (N <= 256 && g_debug[7] != 2) {
+  if (N <= 256) {
     // short sequences: everything resident per (batch, head), no HBM accumulation
     dim3 grid_small(H, B);
     if (causal) {
