@@ -25,6 +25,7 @@ constexpr int AT_HD = 64;
 constexpr int AT_BQ = 128;
 constexpr int AT_BK = 128;
 constexpr int AT_THREADS = 192;        // warps 0-3: softmax/compute, warp 4: TMA, warp 5: MMA + TMEM alloc
+constexpr int AT_BWD_THREADS = 320;    // streaming backward: + warps 6-9, a second compute warpgroup
 constexpr int AT_TILE_BYTES = 128 * 128;  // 128 rows x 64 bf16 = 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -677,7 +678,7 @@ struct BwdSmem {
 };
 
 template <bool CAUSAL>
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const AttnParams p) {
   extern __shared__ uint8_t at_smem_raw[];
@@ -707,9 +708,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
     mbar_init(&q_empty[0], 1); mbar_init(&q_empty[1], 1);
     mbar_init(sdp_full, 1);
-    mbar_init(pds_ready, 128);
+    mbar_init(pds_ready, 256);   // both compute warpgroups
     mbar_init(dq_full, 1);
-    mbar_init(dq_free, 128);
+    mbar_init(dq_free, 256);
     mbar_init(dkv_full, 1);
     fence_barrier_init();
   }
@@ -783,8 +784,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     if (elected) umma_commit(dkv_full);
     __syncwarp();
   } else {
-    const int r = threadIdx.x;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    // two compute warpgroups (warps 0-3 and 6-9) split the 128 key columns of every (key block, query tile) pair:
+    // group g works on the 32-column chunks 2g, 2g+1, reads out dQ chunk g and, at the end, dK (g = 0) / dV (g = 1)
+    const int grp = warp < 4 ? 0 : 1;
+    const int quarter = warp & 3;                 // TMEM lane quarter == warp % 4
+    const int r = quarter * 32 + lane;            // query row within the tile
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     for (int it = 0; it < ntiles; ++it) {
       const int q = (i0 + it) * AT_BQ + r;
       const bool qv = q < p.N;
@@ -804,7 +809,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       mbar_wait(sdp_full, it & 1, 60);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * grp; c < 2 * grp + 2; ++c) {
         uint32_t s[32], dp[32];
         tmem_ld32(tmem_S + lane_off + c * 32, s);
         tmem_ld32(tmem_dP + lane_off + c * 32, dp);
@@ -840,8 +845,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
       mbar_wait(dq_full, it & 1, 61);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = grp;
         uint32_t v[32];
         tmem_ld32(tmem_dQ + lane_off + c * 32, v);
         tmem_ld_wait();
@@ -860,8 +865,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     mbar_wait(dkv_full, 0, 62);
     tc_fence_after();
     const int key = k0 + r;
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {  // 0: dK, 1: dV
+    {
+      const int which = grp;  // 0: dK, 1: dV
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
@@ -1663,10 +1668,10 @@ int b200vit_flash_attn_bwd_dropout(const void* qkv, const void* o, const void* d
   dim3 grid((N + AT_BK - 1) / AT_BK, H, B);
   if (causal) {
     B200_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
-    attn_bwd_kernel<true><<<grid, AT_THREADS, BwdSmem::TOTAL, st>>>(tm_qkv, tm_do, p);
+    attn_bwd_kernel<true><<<grid, AT_BWD_THREADS, BwdSmem::TOTAL, st>>>(tm_qkv, tm_do, p);
   } else {
     B200_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
-    attn_bwd_kernel<false><<<grid, AT_THREADS, BwdSmem::TOTAL, st>>>(tm_qkv, tm_do, p);
+    attn_bwd_kernel<false><<<grid, AT_BWD_THREADS, BwdSmem::TOTAL, st>>>(tm_qkv, tm_do, p);
   }
   B200_CUDA(cudaGetLastError());
   const long long rows = (long long)B * N;
