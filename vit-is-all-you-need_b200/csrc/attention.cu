@@ -42,6 +42,7 @@ struct AttnParams {
   const __nv_bfloat16* o_in;   // [B, N, d]
   const __nv_bfloat16* do_in;  // [B, N, d]
   float* dq_acc;               // [B, N, d] fp32, zeroed
+  const float* dstat;          // [B, H, N] fp32: D = rowsum(dO o O), written by attn_bwd_dstat_kernel (streaming bwd)
   __nv_bfloat16* dqkv;         // [B, N, 3d]
   // dropout on the attention probabilities (dropout_p of SDPA, transformer.py:28); drop_thr == 0: none
   uint32_t drop_seed, drop_thr;
@@ -794,17 +795,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const int q = (i0 + it) * AT_BQ + r;
       const bool qv = q < p.N;
       float lse2 = 0.f, Dq = 0.f;
-      if (qv) {
-        lse2 = p.lse[((long long)b * p.H + hh) * p.N + q] * LOG2E;
-        const uint4* orow = reinterpret_cast<const uint4*>(p.o_in + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD);
-        const uint4* drow = reinterpret_cast<const uint4*>(p.do_in + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 a = orow[c], g = drow[c];
-          const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
-          const float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
-          Dq += a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
-        }
+      if (qv) {  // two scalar loads per row, issued before the S / dP MMAs are waited for (D comes from the pre-pass)
+        lse2 = __ldg(p.lse + ((long long)b * p.H + hh) * p.N + q) * LOG2E;
+        Dq = __ldg(p.dstat + ((long long)b * p.H + hh) * p.N + q);
       }
       mbar_wait(sdp_full, it & 1, 60);
       tc_fence_after();
@@ -1511,6 +1504,36 @@ attn_bwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv_a, const __grid
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// D[b, h, q] = sum_c dO[b, q, h, c] * O[b, q, h, c]: one warp per token row, fully coalesced; every key-block CTA of
+// the streaming backward then needs two scalars per query row instead of re-reading 256 bytes of O and dO.
+__global__ void __launch_bounds__(256) attn_bwd_dstat_kernel(const __nv_bfloat16* __restrict__ o,
+                                                              const __nv_bfloat16* __restrict__ d_o,
+                                                              float* __restrict__ dstat, int B, int N, int H,
+                                                              long long sb, long long sn) {
+  const int d = H * AT_HD;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);   // token index b * N + q
+  if (row >= (long long)B * N) return;
+  const int b = (int)(row / N), q = (int)(row - (long long)b * N);
+  const long long off = ((long long)b * sb + (long long)q * sn) * d;
+  for (int c0 = 0; c0 < d / 8; c0 += 32) {     // 8 elements per lane per step; 8 consecutive lanes = one head
+    const int c = c0 + lane;
+    const bool valid = c < d / 8;              // warp-uniform loop: every lane takes part in the shuffles
+    float acc = 0.f;
+    if (valid) {
+      const uint4 x = *reinterpret_cast<const uint4*>(o + off + c * 8);
+      const uint4 g = *reinterpret_cast<const uint4*>(d_o + off + c * 8);
+      const float2 x0 = unpack_bf16(x.x), x1 = unpack_bf16(x.y), x2 = unpack_bf16(x.z), x3 = unpack_bf16(x.w);
+      const float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
+      acc = x0.x * g0.x + x0.y * g0.y + x1.x * g1.x + x1.y * g1.y + x2.x * g2.x + x2.y * g2.y + x3.x * g3.x + x3.y * g3.y;
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (valid && (lane & 7) == 0) dstat[((long long)b * H + (c >> 3)) * N + q] = acc;
+  }
+}
+
 // dq_acc fp32 [rows, d] -> bf16 into dqkv[:, 0:d] (row pitch 3d)
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
                                        long long rows, int d) {
@@ -1588,7 +1611,8 @@ int b200vit_flash_attn_fwd_dropout(const void* qkv, void* o, float* lse, int B, 
 }
 
 size_t b200vit_flash_attn_bwd_workspace_size(int B, int N, int H) {
-  return N > 256 ? (size_t)B * N * H * AT_HD * sizeof(float) : 0;   // resident kernels (N <= 256): no workspace
+  // streaming kernel: fp32 dQ accumulator [B, N, d] + D statistics [B, H, N]; resident kernels (N <= 256): nothing
+  return N > 256 ? ((size_t)B * N * H * AT_HD + (size_t)B * H * N) * sizeof(float) : 0;
 }
 
 int b200vit_flash_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv,
@@ -1664,7 +1688,15 @@ int b200vit_flash_attn_bwd_dropout(const void* qkv, const void* o, const void* d
     B200_CUDA(cudaGetLastError());
     return OK;
   }
-  B200_CUDA(cudaMemsetAsync(workspace, 0, b200vit_flash_attn_bwd_workspace_size(B, N, H), st));
+  B200_CUDA(cudaMemsetAsync(workspace, 0, (size_t)B * N * d * sizeof(float), st));
+  {
+    float* dstat = (float*)workspace + (size_t)B * N * d;
+    p.dstat = dstat;
+    const long long rows = (long long)B * N;
+    attn_bwd_dstat_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o, dstat,
+                                                                   B, N, H, p.sb, p.sn);
+    B200_CUDA(cudaGetLastError());
+  }
   dim3 grid((N + AT_BK - 1) / AT_BK, H, B);
   if (causal) {
     B200_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL));
