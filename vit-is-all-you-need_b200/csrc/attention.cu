@@ -92,6 +92,21 @@ __device__ __forceinline__ void store_operand_chunk(uint8_t* tile, int row, int 
 // --------------------------------------------------------------------------------------------------
 // Forward
 // --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 struct FwdSmem {
   static constexpr int Q = 0;
   static constexpr int KV = AT_TILE_BYTES;                  // 2 stages x (K | V)
@@ -102,7 +117,8 @@ struct FwdSmem {
 
 template <bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
+                const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t at_smem_raw[];
   uint8_t* smem = at_smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte aligned bases
@@ -301,9 +317,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         for (int i = 0; i < 32; ++i) oacc[c * 32 + i] += __uint_as_float(v[i]);
       }
     }
-    if (q < p.N) {
+    {
+      // the P tile is dead after the last PV MMA: stage O there (swizzled) and leave through one TMA store per warp;
+      // rows beyond the sequence are clipped by the tensor map
       const float inv = p.drop_r / l;   // kept probabilities are scaled by 1 / (1 - p)
-      __nv_bfloat16* orow = p.o + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD;
+      uint8_t* rowp = smem + FwdSmem::P + r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         uint4 w;
@@ -311,9 +329,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         w.y = pack_bf16(oacc[c * 8 + 2] * inv, oacc[c * 8 + 3] * inv);
         w.z = pack_bf16(oacc[c * 8 + 4] * inv, oacc[c * 8 + 5] * inv);
         w.w = pack_bf16(oacc[c * 8 + 6] * inv, oacc[c * 8 + 7] * inv);
-        reinterpret_cast<uint4*>(orow)[c] = w;
+        *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) = w;
       }
-      if (p.lse != nullptr) p.lse[((long long)b * p.H + hh) * p.N + q] = m * LN2 + logf(l);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tm_o, smem + FwdSmem::P + warp * 4096, hh * AT_HD, q0 + warp * 32, b);
+        bulk_commit();
+      }
+      if (q < p.N && p.lse != nullptr) p.lse[((long long)b * p.H + hh) * p.N + q] = m * LN2 + logf(l);
+      if (lane == 0) bulk_wait_all();   // shared memory must stay valid until the store has read it
     }
     }
   }
@@ -338,21 +363,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
 // TMEM columns of tile t (base 256 t): S fp32 [0, ncols), P bf16 [0, ncols/2) (overwrites S behind the reads),
 // O fp32 [128, 192) (S is dead by then).
 // --------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(map)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // One warp: 32 rows x 64 fp32 TMEM columns (scaled per row) -> bf16 -> swizzled staging rows -> one TMA store
 // (box 64 x 32; rows beyond the sequence are clipped by the tensor map).
 __device__ __forceinline__ void bwd2_store_tile(uint32_t tsrc, float sc, uint8_t* stage_rows, bool write_ok,
@@ -1585,13 +1595,13 @@ int b200vit_flash_attn_fwd_dropout(const void* qkv, void* o, float* lse, int B, 
   p.drop_seed = seed; p.drop_thr = dropout_p > 0.f ? drop_threshold(dropout_p) : 0u; p.drop_r = 1.0f / (1.0f - dropout_p);
   dim3 grid((N + AT_BQ - 1) / AT_BQ, H, B);
   cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tm_o;   // O leaves through 32-row TMA stores in every forward kernel
+  rc = make_tmap_bnd(&tm_o, o, B, N, d, seq_first, 32);
+  if (rc != OK) return rc;
   if (!causal && N <= 256 && g_debug[7] == 0) {
     // short sequences: persistent kernel, whole head resident, exact single-shot softmax, P in TMEM
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdShortSmem::TOTAL));
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_short_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdShortSmem::TOTAL));
-    CUtensorMap tm_o;
-    rc = make_tmap_bnd(&tm_o, o, B, N, d, seq_first, 32);
-    if (rc != OK) return rc;
     const int units = B * H;
     const int g = units < num_sms() ? units : num_sms();
     if (p.drop_thr != 0) launch_kernel(attn_fwd_short_kernel<true>, dim3(g), dim3(AS_THREADS), FwdShortSmem::TOTAL, st, 1, tm, tm_o, p);
@@ -1601,10 +1611,10 @@ int b200vit_flash_attn_fwd_dropout(const void* qkv, void* o, float* lse, int B, 
   }
   if (causal) {
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
-    attn_fwd_kernel<true><<<grid, AT_THREADS, FwdSmem::TOTAL, st>>>(tm, p);
+    attn_fwd_kernel<true><<<grid, AT_THREADS, FwdSmem::TOTAL, st>>>(tm, tm_o, p);
   } else {
     B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL));
-    attn_fwd_kernel<false><<<grid, AT_THREADS, FwdSmem::TOTAL, st>>>(tm, p);
+    attn_fwd_kernel<false><<<grid, AT_THREADS, FwdSmem::TOTAL, st>>>(tm, tm_o, p);
   }
   B200_CUDA(cudaGetLastError());
   return OK;
