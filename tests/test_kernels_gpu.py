@@ -197,6 +197,39 @@ def test_flash_attention(ops, B, N, H, causal):
     _attn_case(ops, B, N, H, causal, seed=N + H)
 
 
+@pytest.mark.parametrize("N,spikes", [(197, (150,)), (197, (40, 100, 196)), (65, (64,)), (130, (33, 129))])
+def test_flash_attention_lazy_rescale(ops, N, spikes):
+    """The short-sequence forward exponentiates against the maximum of the FIRST 32-key chunk and only rescales when a
+    later key beats it by more than 2^8: keys with very large norms outside the first chunk force that path (and rows
+    whose scores towards them are negative must be unaffected)."""
+    B, H = 2, 2
+    rng = np.random.default_rng(N + len(spikes))
+    d = H * 64
+    qkv = rng.standard_normal((B, N, 3, H, 64)).astype(np.float32)
+    for sp in spikes:
+        qkv[:, sp, 1] *= 9.0          # huge keys late in the sequence
+    qkv = bf16_round(qkv)
+    q, k, v = (np.transpose(qkv[:, :, i], (0, 2, 1, 3)).astype(np.float64) for i in range(3))
+    s = (q @ np.swapaxes(k, -1, -2)) / 8.0 * math.log2(math.e)
+    assert (s.max(-1) - s[..., :32].max(-1)).max() > 8.0, "the case must exercise the rescaling path"
+    o_ref, cache = O.sdpa_fwd(q, k, v, False)
+    o, lse = ops.flash_attn_fwd(to_dev(qkv, torch.bfloat16), B, N, H, False)
+    assert_close_bf16(o, np.transpose(o_ref, (0, 2, 1, 3)).reshape(B, N, d), f"attention fwd (lazy rescale) N={N}", rel=1.5e-2)
+    sn = (q @ np.swapaxes(k, -1, -2)) / 8.0
+    mx = sn.max(-1, keepdims=True)
+    lse_ref = (mx + np.log(np.exp(sn - mx).sum(-1, keepdims=True)))[..., 0]
+    assert_close_bf16(lse, lse_ref, "lse (lazy rescale)", rel=1e-4)
+    do = bf16_round(rng.standard_normal((B, N, H, 64)).astype(np.float32))
+    dq_ref, dk_ref, dv_ref = O.sdpa_bwd(np.transpose(do, (0, 2, 1, 3)).astype(np.float64), cache)
+    dqkv_ref = np.stack([np.transpose(t, (0, 2, 1, 3)) for t in (dq_ref, dk_ref, dv_ref)], axis=2).reshape(B, N, 3 * d)
+    dqkv = ops.flash_attn_bwd(to_dev(qkv, torch.bfloat16), o, to_dev(do.reshape(B, N, d), torch.bfloat16), lse, B, N, H, False)
+    got = dqkv.float().cpu().numpy()
+    for i, nm in enumerate(("dq", "dk", "dv")):
+        ref = dqkv_ref[:, :, i * d:(i + 1) * d]
+        err = np.abs(got[:, :, i * d:(i + 1) * d] - ref).max() / (np.abs(ref).max() + 1e-12)
+        assert err < 2e-2, f"attention bwd after lazy-rescale fwd {nm} N={N}: {err:.3e}"
+
+
 @pytest.mark.parametrize("B,N,H,causal,p", [(2, 65, 3, False, 0.15), (3, 197, 2, False, 0.15), (1, 128, 2, False, 0.5),
                                             (2, 257, 1, False, 0.15), (1, 240, 1, False, 0.3), (1, 200, 2, True, 0.15),
                                             (1, 384, 1, True, 0.1)])

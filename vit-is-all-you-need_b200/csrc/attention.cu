@@ -548,10 +548,15 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
         tc_fence_after();
         float l = 0.f, m2 = 0.f;
         if (warp_has_rows) {
-          // pass 1: row maximum over the valid keys (two register buffers, statically indexed)
-          float mx = -INFINITY;
+          // SINGLE pass over S (the kernel is bound by TMEM read bandwidth, ~64 B/clk/SM: a separate row-maximum pass
+          // costs as much as the exponentials).  The reference maximum is the maximum of the FIRST 32-key chunk; later
+          // chunks are exponentiated against it as long as no row of the warp exceeds it by more than 2^TAU (P then
+          // stays <= 256, exact in bf16's range, and O / l is invariant to the choice of the reference).  In the rare
+          // other case the chunks already written are rescaled in place and the reference is raised (lazy rescaling).
+          constexpr float TAU = 8.0f;
           uint32_t va[32], vb[32];
-          auto max_chunk = [&](const uint32_t (&x)[32], int c) {
+          auto chunk_max = [&](const uint32_t (&x)[32], int c) -> float {
+            float mx = -INFINITY;
             if ((c + 1) * 32 <= p.N) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(x[i]));
@@ -559,26 +564,27 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
 #pragma unroll
               for (int i = 0; i < 32; ++i) mx = fmaxf(mx, c * 32 + i < p.N ? __uint_as_float(x[i]) : -INFINITY);
             }
+            return mx * p.scale_log2e;
           };
-          if (nch > 0) tmem_ld32(tS, va);
-          for (int c = 0; c < nch; c += 2) {
-            tmem_ld_wait();
-            if (c + 1 < nch) tmem_ld32(tS + (c + 1) * 32, vb);
-            max_chunk(va, c);
-            if (c + 1 < nch) {
+          // raise the reference to cover `cm` (per row) and rescale the `nw` 16-column P pieces already in TMEM
+          auto raise_reference = [&](float cm, int nw) {
+            const float m_new = fmaxf(m2, cm);
+            const float alpha = ex2_approx(m2 - m_new);   // 1 for the rows whose maximum did not move
+            l *= alpha;
+            m2 = m_new;
+            tmem_st_wait();
+            for (int cc = 0; cc < nw; ++cc) {
+              uint32_t w[16];
+              tmem_ld16(tS + cc * 16, w);
               tmem_ld_wait();
-              if (c + 2 < nch) tmem_ld32(tS + (c + 2) * 32, va);
-              max_chunk(vb, c + 1);
-            }
-          }
-          if (tail16) {
-            uint32_t w[16];
-            tmem_ld16(tS + nch * 32, w);
-            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, nch * 32 + i < p.N ? __uint_as_float(w[i]) : -INFINITY);
-          }
-          m2 = mx * p.scale_log2e;
+              for (int i = 0; i < 16; ++i) {
+                const float2 f = unpack_bf16(w[i]);
+                w[i] = pack_bf16(f.x * alpha, f.y * alpha);
+              }
+              tmem_st16(tS + cc * 16, w);
+            }
+          };
           // pass 2: probabilities -> packed bf16 written over the S columns already consumed
           auto exp_chunk = [&](const uint32_t (&x)[32], int c) {
             uint32_t w[16];
@@ -614,21 +620,35 @@ attn_fwd_short_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
             }
             tmem_st16(tS + c * 16, w);
           };
+          auto step = [&](const uint32_t (&x)[32], int c) {
+            const float cm = chunk_max(x, c);
+            if (c == 0) m2 = cm;
+            else if (__any_sync(0xffffffffu, cm > m2 + TAU)) raise_reference(cm, c * 2);
+            exp_chunk(x, c);
+          };
           if (nch > 0) tmem_ld32(tS, va);
           for (int c = 0; c < nch; c += 2) {
             tmem_ld_wait();
             if (c + 1 < nch) tmem_ld32(tS + (c + 1) * 32, vb);
-            exp_chunk(va, c);
+            step(va, c);
             if (c + 1 < nch) {
               tmem_ld_wait();
               if (c + 2 < nch) tmem_ld32(tS + (c + 2) * 32, va);
-              exp_chunk(vb, c + 1);
+              step(vb, c + 1);
             }
           }
           if (tail16) {
             uint32_t x[16], w[16];
             tmem_ld16(tS + nch * 32, x);
             tmem_ld_wait();
+            {
+              float mx = -INFINITY;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) mx = fmaxf(mx, nch * 32 + i < p.N ? __uint_as_float(x[i]) : -INFINITY);
+              const float cm = mx * p.scale_log2e;
+              if (nch == 0) m2 = cm;
+              else if (__any_sync(0xffffffffu, cm > m2 + TAU)) raise_reference(cm, nch * 2);
+            }
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
               float p0 = ex2_approx(fmaf(__uint_as_float(x[i]), p.scale_log2e, -m2));
