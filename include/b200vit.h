@@ -94,6 +94,11 @@ int b200vit_layernorm_fwd(const float* x, const void* add_bf16, float* x_out, co
 int b200vit_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float* x, const float* mean,
                           const float* rstd, const float* gamma, const float* dres, float* dx, void* dx_bf16,
                           float* dgamma, float* dbeta, int M, int d, void* stream);
+/* backward of the affine-free LayerNorm (transformer.py:43-44) from the SAVED bf16 forward output xhat = LN(x)
+ * instead of the fp32 row and its mean: dx = dres (optional) + rstd * (dy - mean(dy) - xhat * mean(dy * xhat));
+ * 14 instead of 16 bytes per element and the fp32 residual rows need not be kept for backward.               */
+int b200vit_layernorm_bwd_xhat(const void* dy_bf16, const void* xhat_bf16, const float* rstd, const float* dres,
+                               float* dx, void* dx_bf16, int M, int d, void* stream);
 /* out[N](f32) (+)= column sums of a[M,N](bf16): bias gradients of nn.Linear                                  */
 int b200vit_colsum_bf16(const void* a, float* out, int M, int N, int accumulate, void* stream);
 int b200vit_colsum_f32(const float* a, float* out, int rows, int n, void* stream);

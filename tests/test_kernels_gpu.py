@@ -162,6 +162,30 @@ def test_layernorm_fwd_bwd(ops, M, d, affine):
         assert_close_bf16(db, db_ref, "dbeta", rel=1e-4)
 
 
+@pytest.mark.parametrize("M,d", [(197 * 5 + 3, 768), (1029, 512), (301, 1024), (65 * 4, 192), (7, 64)])
+def test_layernorm_bwd_from_saved_xhat(ops, M, d):
+    # affine-free LN backward rebuilt from the saved bf16 forward output (x-hat) and rstd (transformer.py:43-44):
+    # exact (fp32 tolerance) against the oracle formula evaluated on the SAME bf16 x-hat, and within 2e-3 of max|dx|
+    # of the oracle backward that uses the unrounded x-hat (the cost of the 2-byte operand, stated here)
+    rng = np.random.default_rng(M * 3 + d)
+    x = rng.standard_normal((M, d)).astype(np.float32) * 2 + 0.5
+    dy = bf16_round(rng.standard_normal((M, d)).astype(np.float32))
+    dres = rng.standard_normal((M, d)).astype(np.float32)
+    _, cache = O.layer_norm_fwd(x.astype(np.float64), None, None)
+    dx_ref, _, _ = O.layer_norm_bwd(dy.astype(np.float64), cache)
+    y, _, mean, rstd, _ = ops.layernorm_fwd(to_dev(x))
+    xh = y.float().cpu().numpy().astype(np.float64)
+    rs = rstd.cpu().numpy().astype(np.float64)[:, None]
+    g = dy.astype(np.float64)
+    same_xhat = rs * (g - g.mean(-1, keepdims=True) - xh * (g * xh).mean(-1, keepdims=True))
+    for use_dres in (True, False):
+        dx, dxb = ops.layernorm_bwd_xhat(to_dev(dy, torch.bfloat16), y, rstd, dres=to_dev(dres) if use_dres else None)
+        add = dres if use_dres else 0.0
+        assert_close_bf16(dx, same_xhat + add, "LN bwd (x-hat) dx vs same-operand formula", rel=2e-5)
+        assert_close_bf16(dx, dx_ref + add, "LN bwd (x-hat) dx vs fp32-x-hat oracle", rel=2e-3)
+        assert_close_bf16(dxb, dx_ref + add, "LN bwd (x-hat) dx bf16", rel=5e-3)
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def _attn_case(ops, B, N, H, causal, seed):
     rng = np.random.default_rng(seed)

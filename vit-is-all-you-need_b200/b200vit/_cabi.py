@@ -60,6 +60,7 @@ _SIGNATURES = {
     "b200vit_flash_attn_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "b200vit_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P]),
     "b200vit_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "b200vit_layernorm_bwd_xhat": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "b200vit_colsum_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
     "b200vit_colsum_f32": (_I, [_P, _P, _I, _I, _P]),
     "b200vit_cast_f32_bf16": (_I, [_P, _P, _L, _P]),

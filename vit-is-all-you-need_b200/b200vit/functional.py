@@ -113,13 +113,15 @@ def layer_forward(x0, P: LayerParams, B, N, H, causal, save, dropout=(0.0, 0.0))
         x2 = ops.gemm_bias_dropout_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1, p_mlp, seeds[1])
     else:
         x2 = ops.gemm_bias_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1)
-    saved = (x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g, seeds) if save else None
+    # backward rebuilds LN' from the saved bf16 outputs a / b (= x-hat: the LN is affine-free) and rstd, so the fp32
+    # residual rows x0 / x1 and the means are not kept
+    saved = (rstd1, a, qkv, o, lse, rstd2, b, u, g, seeds) if save else None
     return x2, saved
 
 
 def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_dx=True, dropout=(0.0, 0.0), sink=None):
     """dx2: [B*N, d] fp32 (dx2_bf16: optional bf16 copy).  Returns (dx0, dx0_bf16, grads in LayerParams order)."""
-    x0, mean1, rstd1, a, qkv, o, lse, x1, mean2, rstd2, b, u, g, seeds = saved
+    rstd1, a, qkv, o, lse, rstd2, b, u, g, seeds = saved
     p_attn, p_mlp = dropout
     if p_mlp > 0.0:
         dv = ops.dropout_cast_bf16(dx2, p_mlp, seeds[1])   # gradient through nn.Dropout, same mask as forward
@@ -131,14 +133,14 @@ def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_d
     d_fc1_w, d_fc1_b = ops.gemm_wgrad(du, b, out=_slot(sink, P.fc1_w), bias_out=_slot(sink, P.fc1_b), want_bias=True)
     _ready(sink, P.fc1_w, P.fc1_b)
     db = ops.gemm_dgrad(du, bf16_of(P.fc1_w))
-    dx1, dx1_bf16, _, _ = ops.layernorm_bwd(db, x1, mean2, rstd2, dres=dx2, want_bf16=True)
+    dx1, dx1_bf16 = ops.layernorm_bwd_xhat(db, b, rstd2, dres=dx2, want_bf16=True)
     dqkv = ops.flash_attn_bwd(qkv, o, dx1_bf16.view(B, N, -1), lse, B, N, H, causal, dropout_p=p_attn, seed=seeds[0]).view(B * N, -1)
     d_qkv_w, d_qkv_b = ops.gemm_wgrad(dqkv, a, out=_slot(sink, P.qkv_w), bias_out=_slot(sink, P.qkv_b), want_bias=True)
     _ready(sink, P.qkv_w, P.qkv_b)
     dx0 = dx0_bf16 = None
     if need_dx:
         da = ops.gemm_dgrad(dqkv, bf16_of(P.qkv_w))
-        dx0, dx0_bf16, _, _ = ops.layernorm_bwd(da, x0, mean1, rstd1, dres=dx1, want_bf16=True)
+        dx0, dx0_bf16 = ops.layernorm_bwd_xhat(da, a, rstd1, dres=dx1, want_bf16=True)
     grads = (d_qkv_w, d_qkv_b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b)
     if sink is not None:
         # gradients already sit in their all-reduce bucket slots and have been marked ready: hand autograd None so

@@ -235,6 +235,18 @@ def layernorm_bwd(dy, x, mean, rstd, gamma=None, dres=None, want_bf16=True, affi
     return dx, dxb, dg, db
 
 
+def layernorm_bwd_xhat(dy, xhat, rstd, dres=None, want_bf16=True):
+    """Backward of the affine-free LayerNorm from its saved bf16 output (xhat) and rstd; returns (dx fp32, dx bf16)."""
+    d = xhat.shape[-1]
+    M = xhat.numel() // d
+    dx = torch.empty(xhat.shape, device=xhat.device, dtype=F32)
+    dxb = torch.empty(xhat.shape, device=xhat.device, dtype=BF16) if want_bf16 else None
+    nbytes = M * d * (2 + 2 + (4 if dres is not None else 0) + 4 + (2 if want_bf16 else 0)) + 4 * M
+    _call("b200vit_layernorm_bwd_xhat", xhat, ptr(_chk(dy, BF16, "dy")), ptr(_chk(xhat, BF16, "xhat")), ptr(_chk(rstd, F32, "rstd")),
+          ptr(dres), ptr(dx), ptr(dxb), M, d, stream_ptr(), hbm_bytes=float(nbytes))
+    return dx, dxb
+
+
 def colsum_bf16(a, out=None, accumulate=False):
     M, N = a.shape
     if out is None:

@@ -90,6 +90,7 @@ struct LnBwdArgs {
   const float* gamma; const float* dres;
   float* dx; __nv_bfloat16* dx_bf16; float* dgamma; float* dbeta;
   int M, d;
+  const __nv_bfloat16* xhat;  // when set (affine-free LN only): the saved bf16 normalised rows replace x / mean
 };
 
 template <bool AFFINE>
@@ -102,14 +103,21 @@ __global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(const LnBwdArgs a) {
   for (int i = 0; i < LN_MAXCH; ++i) { accg[i] = make_float4(0, 0, 0, 0); accb[i] = make_float4(0, 0, 0, 0); }
 
   for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < a.M; row += (long long)gridDim.x * LN_WARPS) {
-    const float mean = a.mean[row], rstd = a.rstd[row];
+    const float mean = a.xhat != nullptr ? 0.f : a.mean[row], rstd = a.rstd[row];
     float4 xh[LN_MAXCH], g[LN_MAXCH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < LN_MAXCH; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
-        const float4 xv = reinterpret_cast<const float4*>(a.x + row * a.d)[c];
+        float4 xv;
+        if (a.xhat != nullptr) {
+          const uint2 u = *reinterpret_cast<const uint2*>(a.xhat + row * a.d + c * 4);
+          const float2 p0 = unpack_bf16(u.x), p1 = unpack_bf16(u.y);
+          xv = make_float4(p0.x, p0.y, p1.x, p1.y);
+        } else {
+          xv = reinterpret_cast<const float4*>(a.x + row * a.d)[c];
+        }
         float4 dyv;
         if (a.dy != nullptr) {
           const uint2 u = *reinterpret_cast<const uint2*>(a.dy + row * a.d + c * 4);
@@ -118,8 +126,12 @@ __global__ void __launch_bounds__(LN_THREADS) ln_bwd_kernel(const LnBwdArgs a) {
         } else {
           dyv = reinterpret_cast<const float4*>(a.dy_f32 + row * a.d)[c];
         }
-        xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
-        xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
+        if (a.xhat != nullptr) {
+          xh[i] = xv;
+        } else {
+          xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
+          xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
+        }
         if (affine_grads) {
           accg[i].x += dyv.x * xh[i].x; accg[i].y += dyv.y * xh[i].y;
           accg[i].z += dyv.z * xh[i].z; accg[i].w += dyv.w * xh[i].w;
@@ -265,7 +277,9 @@ __global__ void __launch_bounds__(LNF_THREADS) ln_fwd_fast_kernel(const LnFwdArg
 }
 
 // dx = dres + LN'(dy), affine-free or with gamma (no parameter gradients here), bf16 dy, optional bf16 copy.
-template <int CH, bool GAMMA>
+// XHAT: x-hat comes from the saved bf16 output of the (affine-free) forward instead of being rebuilt from the fp32
+// row and its mean -- 14 instead of 16 bytes per element, and the fp32 residual rows need not be kept for backward.
+template <int CH, bool GAMMA, bool XHAT>
 __global__ void __launch_bounds__(LNF_THREADS) ln_bwd_fast_kernel(const LnBwdArgs a) {
   constexpr int D = CH * 128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -273,13 +287,22 @@ __global__ void __launch_bounds__(LNF_THREADS) ln_bwd_fast_kernel(const LnBwdArg
   pdl_wait();
   pdl_trigger();
   if (row >= a.M) return;
-  const float mean = __ldg(a.mean + row), rstd = __ldg(a.rstd + row);
-  const float* xr = a.x + row * D + lane * 4;
+  const float rstd = __ldg(a.rstd + row);
   const __nv_bfloat16* dyr = a.dy + row * D + lane * 4;
   float4 xh[CH], r[CH];
   uint2 u[CH];
+  [[maybe_unused]] uint2 xq[CH];
+  [[maybe_unused]] float nm = 0.f;
+  if constexpr (XHAT) {
+    const __nv_bfloat16* hr = a.xhat + row * D + lane * 4;
 #pragma unroll
-  for (int i = 0; i < CH; ++i) xh[i] = ld_stream4(xr + i * 128);
+    for (int i = 0; i < CH; ++i) xq[i] = ld_stream2(hr + i * 128);
+  } else {
+    nm = -__ldg(a.mean + row) * rstd;
+    const float* xr = a.x + row * D + lane * 4;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) xh[i] = ld_stream4(xr + i * 128);
+  }
 #pragma unroll
   for (int i = 0; i < CH; ++i) u[i] = ld_stream2(dyr + i * 128);
   if (a.dres != nullptr) {
@@ -292,7 +315,6 @@ __global__ void __launch_bounds__(LNF_THREADS) ln_bwd_fast_kernel(const LnBwdArg
   }
   float4 g[CH];
   float s1 = 0.f, s2 = 0.f;
-  const float nm = -mean * rstd;
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
     const float2 p0 = unpack_bf16(u[i].x), p1 = unpack_bf16(u[i].y);
@@ -301,8 +323,13 @@ __global__ void __launch_bounds__(LNF_THREADS) ln_bwd_fast_kernel(const LnBwdArg
       const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma) + lane + 32 * i);
       g[i].x *= gm.x; g[i].y *= gm.y; g[i].z *= gm.z; g[i].w *= gm.w;
     }
-    xh[i].x = fmaf(xh[i].x, rstd, nm); xh[i].y = fmaf(xh[i].y, rstd, nm);
-    xh[i].z = fmaf(xh[i].z, rstd, nm); xh[i].w = fmaf(xh[i].w, rstd, nm);
+    if constexpr (XHAT) {
+      const float2 h0 = unpack_bf16(xq[i].x), h1 = unpack_bf16(xq[i].y);
+      xh[i] = make_float4(h0.x, h0.y, h1.x, h1.y);
+    } else {
+      xh[i].x = fmaf(xh[i].x, rstd, nm); xh[i].y = fmaf(xh[i].y, rstd, nm);
+      xh[i].z = fmaf(xh[i].z, rstd, nm); xh[i].w = fmaf(xh[i].w, rstd, nm);
+    }
     s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
     s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
   }
@@ -352,8 +379,9 @@ static bool try_ln_fwd_fast(const LnFwdArgs& a, cudaStream_t st) {
 template <int CH>
 static bool launch_ln_bwd_fast(const LnBwdArgs& a, cudaStream_t st) {
   const int grid = (a.M + LNF_WARPS - 1) / LNF_WARPS;
-  if (a.gamma != nullptr) launch_kernel(ln_bwd_fast_kernel<CH, true>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
-  else                    launch_kernel(ln_bwd_fast_kernel<CH, false>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
+  if (a.xhat != nullptr)  launch_kernel(ln_bwd_fast_kernel<CH, false, true>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
+  else if (a.gamma != nullptr) launch_kernel(ln_bwd_fast_kernel<CH, true, false>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
+  else                    launch_kernel(ln_bwd_fast_kernel<CH, false, false>, dim3(grid), dim3(LNF_THREADS), 0, st, 1, a);
   return true;
 }
 static bool try_ln_bwd_fast(const LnBwdArgs& a, cudaStream_t st) {
@@ -429,7 +457,7 @@ int b200vit_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float*
     B200_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * d, st));
     B200_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * d, st));
   }
-  LnBwdArgs a{(const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, dres, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, M, d};
+  LnBwdArgs a{(const __nv_bfloat16*)dy_bf16, dy_f32, x, mean, rstd, gamma, dres, dx, (__nv_bfloat16*)dx_bf16, dgamma, dbeta, M, d, nullptr};
   if (try_ln_bwd_fast(a, st)) {
     B200_CUDA(cudaGetLastError());
     return OK;
@@ -439,6 +467,24 @@ int b200vit_layernorm_bwd(const void* dy_bf16, const float* dy_f32, const float*
   const int grid = blocks < cap ? blocks : cap;
   if (dgamma) ln_bwd_kernel<true><<<grid, LN_THREADS, 0, st>>>(a);
   else        ln_bwd_kernel<false><<<grid, LN_THREADS, 0, st>>>(a);
+  B200_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int b200vit_layernorm_bwd_xhat(const void* dy_bf16, const void* xhat_bf16, const float* rstd, const float* dres,
+                               float* dx, void* dx_bf16, int M, int d, void* stream) {
+  B200_REQUIRE(dy_bf16 && xhat_bf16 && rstd && dx, "layernorm_bwd_xhat: null pointer");
+  B200_REQUIRE(M > 0 && d > 0 && d % 4 == 0 && d <= 128 * LN_MAXCH, "layernorm_bwd_xhat: d=%d must be a multiple of 4 and <= %d", d, 128 * LN_MAXCH);
+  cudaStream_t st = (cudaStream_t)stream;
+  LnBwdArgs a{(const __nv_bfloat16*)dy_bf16, nullptr, nullptr, nullptr, rstd, nullptr, dres, dx, (__nv_bfloat16*)dx_bf16,
+              nullptr, nullptr, M, d, (const __nv_bfloat16*)xhat_bf16};
+  if (try_ln_bwd_fast(a, st)) {
+    B200_CUDA(cudaGetLastError());
+    return OK;
+  }
+  const int blocks = (M + LN_WARPS - 1) / LN_WARPS;
+  const int grid = blocks < num_sms() * 16 ? blocks : num_sms() * 16;
+  ln_bwd_kernel<false><<<grid, LN_THREADS, 0, st>>>(a);
   B200_CUDA(cudaGetLastError());
   return OK;
 }
