@@ -138,6 +138,18 @@ int b200vit_vq_bwd(const float* x, const float* codebook, const long long* indic
                    const float* coef, long long R, int D, int K, long long inner, long long elem_stride,
                    long long outer_stride, int flags, float* dx, float* dcodebook, void* stream);
 
+/* ---- fused multi-tensor AdamW + bf16 operand refresh (torch.optim.AdamW at train_vit.py:82,105, ------------
+ * train_titok.py:134,160, train_videogpt.py:107,134; arithmetic of torch/optim/adam.py::_single_tensor_adam)
+ * tensors: device array of { float* p; const float* g; float* m; float* v; bf16* w16 (or NULL); long long n } ;
+ * chunks: device array of { int tensor; int chunk_index } -- one CTA per b200vit_adamw_chunk_elems() elements.
+ * step: 1-based step number (host) -- or step_dev: device fp32 counter that the call advances (CUDA-graph capture,
+ * GradScaler).  grad_scale / found_inf: optional device scalars of torch.amp.GradScaler: g /= *grad_scale; when
+ * *found_inf != 0 nothing (not even the counter) changes.                                                     */
+int b200vit_adamw_chunk_elems(void);
+int b200vit_adamw_step(const void* tensors, const void* chunks, int n_chunks, double lr, double beta1, double beta2,
+                       double eps, double weight_decay, long long step, float* step_dev, const float* grad_scale,
+                       const float* found_inf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

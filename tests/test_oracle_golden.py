@@ -183,3 +183,31 @@ def test_c_oracle_vector_quantizer(golden_dir, tag, l2):
                        gather_normalized=l2, channels_first=True)
     _close(dz, g[f"{tag}_dzin"], rtol=1e-4, atol=1e-6)
     _close(dE, g[f"{tag}_dE"], rtol=1e-4, atol=1e-7)
+
+
+def test_adamw_oracle(golden_dir):
+    """oracle/adamw_oracle.py against trajectories of torch.optim.AdamW itself (tests/golden/make_golden_adamw.py)."""
+    from oracle import adamw_oracle as A
+    g = _load(golden_dir, "adamw.npz")
+    b1, b2 = (float(v) for v in g["betas"])
+    for i in range(int(g["n_tensors"])):
+        p = g[f"p0_{i}"].copy()
+        m = np.zeros_like(p)
+        v = np.zeros_like(p)
+        for s in range(int(g["steps"])):
+            p, m, v, took = A.adamw_step(p, g[f"g{s}_{i}"], m, v, s + 1, float(g["lrs"][s]), b1, b2, float(g["eps"]),
+                                         float(g["weight_decay"]))
+            assert took
+            # fp32 op-for-op restatement: a few ulp of the parameter scale (torch's CPU kernels contract some mul+add)
+            np.testing.assert_allclose(p, g[f"p{s + 1}_{i}"], rtol=2e-6, atol=2e-8)
+        m_ref, v_ref = g[f"m{int(g['steps'])}_{i}"], g[f"v{int(g['steps'])}_{i}"]
+        np.testing.assert_allclose(m, m_ref, rtol=2e-6, atol=5e-7 * np.abs(m_ref).max())  # lerp cancels near zero
+        np.testing.assert_allclose(v, v_ref, rtol=2e-6, atol=5e-7 * np.abs(v_ref).max())
+    # GradScaler protocol: found_inf skips everything; grad_scale divides the gradient
+    p0, g0 = g["p0_1"], g["g0_1"]
+    z = np.zeros_like(p0)
+    p1, m1, v1, took = A.adamw_step(p0, g0, z, z, 1, 1e-3, found_inf=1.0)
+    assert not took and np.array_equal(p1, p0) and not m1.any() and not v1.any()
+    pa, ma, va, _ = A.adamw_step(p0, g0 * np.float32(1024.0), z, z, 1, 1e-3, grad_scale=1024.0)
+    pb, mb, vb, _ = A.adamw_step(p0, g0, z, z, 1, 1e-3)
+    np.testing.assert_allclose(pa, pb, rtol=1e-6, atol=1e-9)

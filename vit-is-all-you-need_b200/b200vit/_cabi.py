@@ -33,7 +33,7 @@ def declared_symbols(header_path: str = HEADER_PATH):
     return sorted(set(re.findall(r"\b(b200vit_[a-z0-9_]+)\s*\(", text)))
 
 
-_P, _I, _L, _F, _Z = c_void_p, c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
+_P, _I, _L, _F, _Z, _D = c_void_p, c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t, ctypes.c_double
 
 # argument types of every entry point in include/b200vit.h (ctypes would otherwise guess c_int for ints)
 _SIGNATURES = {
@@ -68,6 +68,8 @@ _SIGNATURES = {
     "b200vit_patch_embed_bwd_reduce": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "b200vit_im2col_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "b200vit_col2im_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200vit_adamw_chunk_elems": (_I, []),
+    "b200vit_adamw_step": (_I, [_P, _P, _I, _D, _D, _D, _D, _D, _L, _P, _P, _P, _P]),
     "b200vit_vq_workspace_size": (_Z, [_L, _I, _I]),
     "b200vit_vq_fwd": (_I, [_P, _P, _L, _I, _I, _L, _L, _L, _I, _F, _P, _P, _P, _P, _Z, _P]),
     "b200vit_vq_bwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _L, _L, _L, _I, _P, _P, _P]),

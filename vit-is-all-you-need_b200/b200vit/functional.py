@@ -15,15 +15,42 @@ F32 = torch.float32
 # ------------------------------------------------------------------------------------------------------------
 # bf16 operand cache for fp32 parameters (refreshed when the optimiser has touched the parameter)
 # ------------------------------------------------------------------------------------------------------------
+# torch.optim.*(fused=True) updates parameters through torch._fused_*_ ops that do NOT bump Tensor._version (checked on
+# torch 2.11: AdamW(fused=True).step() leaves p._version unchanged, foreach / single-tensor add 2), so the version
+# counter alone would leave the bf16 operands stale for ever.  A global optimizer-step post-hook therefore advances an
+# epoch that is part of the cache key: after ANY optimizer step every cached operand is re-cast on next use.
+# b200vit.optim.AdamW writes the refreshed bf16 operands itself and is exempt (it re-keys the caches it has updated).
+_WEIGHT_EPOCH = 0
+
+
+def _optimizer_stepped(optimizer, *_args, **_kwargs):
+    global _WEIGHT_EPOCH
+    if not getattr(optimizer, "_b200_refreshes_bf16", False):
+        _WEIGHT_EPOCH += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_post_hook  # noqa: E402
+
+_register_step_post_hook(_optimizer_stepped)
+
+
+def bf16_key(p: torch.Tensor):
+    return (_WEIGHT_EPOCH, p._version, p.data_ptr())
+
+
 def bf16_of(p: torch.Tensor) -> torch.Tensor:
-    key = (p._version, p.data_ptr())
+    key = bf16_key(p)
     cached = getattr(p, "_b200_bf16", None)
     if cached is not None and cached[0] == key:
         return cached[1]
     src = p.detach()
     if src.dtype != F32:
         src = src.float()
-    t = ops.cast_bf16(src.contiguous())
+    src = src.contiguous()
+    if cached is not None and cached[1].shape == src.shape and not torch.cuda.is_current_stream_capturing():
+        t = ops.cast_bf16(src, out=cached[1])   # refresh in place: the operand keeps its address from step to step
+    else:
+        t = ops.cast_bf16(src)
     try:
         p._b200_bf16 = (key, t)
     except Exception:  # pragma: no cover  (tensors that refuse attributes)

@@ -7,14 +7,12 @@ allocates nothing and never synchronises, so a step can be captured once and rep
     step = GraphedTrainStep(model, optimizer, loss_fn, example_inputs, example_targets)
     loss = step(images, labels)        # copies into the static buffers, replays the graph, returns the loss tensor
 
-Constraints (the usual CUDA-graph ones): fixed shapes; the optimizer must be capturable (torch.optim.AdamW(...,
-capturable=True) or fused=True on recent PyTorch); dropout masks are functions of host-generated seeds that get baked
+Constraints (the usual CUDA-graph ones): fixed shapes; the optimizer must be capturable (b200vit.optim.AdamW(...,
+capturable=True) or torch.optim.AdamW(..., capturable=True)); dropout masks are functions of host-generated seeds that get baked
 into the graph, so with dropout > 0 a replay repeats the captured masks -- capture is therefore refused for dropout > 0;
 data-parallel wrappers are not captured (their bucket bookkeeping lives on the host).
 """
 import torch
-
-from . import functional as Fn
 
 
 class GraphedTrainStep:
@@ -65,4 +63,3 @@ class GraphedTrainStep:
 
 
 __all__ = ["GraphedTrainStep"]
-_ = Fn  # (functional is imported for its side-effect-free helpers; kept to make the dependency explicit)

@@ -10,6 +10,8 @@ What it does:
     train_vit_vqgan.py:45) are swapped at class-creation time through builtins.__build_class__;
   * torch.nn.Conv2d becomes modules.PatchConv2d, a subclass that routes patchify-shaped convolutions (kernel == stride)
     through the im2col + tcgen05 GEMM path and is otherwise nn.Conv2d;
+  * torch.optim.AdamW becomes b200vit.optim.AdamW (one fused multi-tensor launch that also refreshes the bf16 GEMM operands;
+    same constructor, state_dict layout and GradScaler protocol; B200VIT_TORCH_ADAMW=1 keeps torch's);
   * stubs two imports the scripts never use (lpips, vector_quantize_pytorch.FSQ) when they are not installed,
     disables wandb, and (B200VIT_SYNTHETIC=1) replaces the hard-coded ImageNet loaders with synthetic ones.
 """
@@ -76,6 +78,17 @@ def install_conv_swap():
     return orig
 
 
+def install_optimizer_swap():
+    """torch.optim.AdamW -> b200vit.optim.AdamW (train_vit.py:82, train_titok.py:134, train_vit_vqgan.py:131,
+    train_videogpt.py:107 all call torch.optim.AdamW(model.parameters(), lr=..., weight_decay=...))."""
+    import torch
+
+    from . import optim
+    orig = torch.optim.AdamW
+    torch.optim.AdamW = optim.AdamW
+    return orig
+
+
 def install_synthetic_loaders():
     """datasets.get_imagenet_loaders has a hard-coded dataset root (datasets.py:7,23); benchmarks and smoke runs
     use synthetic tensors of the same shapes instead."""
@@ -111,6 +124,8 @@ def main(argv=None):
         install_synthetic_loaders()
     orig = install_class_swap()
     install_conv_swap()
+    if os.environ.get("B200VIT_TORCH_ADAMW", "0") != "1":
+        install_optimizer_swap()
     sys.argv = [script] + argv[1:]
     try:
         runpy.run_path(script, run_name="__main__")

@@ -263,9 +263,10 @@ def colsum_f32(a):
     return out
 
 
-def cast_bf16(t):
+def cast_bf16(t, out=None):
     t = _chk(t, F32, "t")
-    out = torch.empty(t.shape, device=t.device, dtype=BF16)
+    if out is None:
+        out = torch.empty(t.shape, device=t.device, dtype=BF16)
     if t.numel() % 4 == 0:
         _call("b200vit_cast_f32_bf16", t, ptr(t), ptr(out), t.numel(), stream_ptr())
     else:
