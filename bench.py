@@ -207,7 +207,7 @@ def run_gpu_arm(args):
         optim = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2, fused=True)
     else:   # one fused multi-tensor launch that also refreshes the bf16 GEMM operands (csrc/optim.cu)
         optim = b200_optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2)
-    loss_fn = torch.nn.CrossEntropyLoss()
+    loss_fn = M.CrossEntropyLoss()   # drop-in for nn.CrossEntropyLoss() (train_vit.py:81): fused kernels, bf16 logits in
 
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     n_host = 2
@@ -220,7 +220,7 @@ def run_gpu_arm(args):
         optim.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             pred = wrapped(images)
-            loss = loss_fn(pred.float(), labels)
+            loss = loss_fn(pred, labels)
         if after_forward is not None:
             after_forward(loss)
         loss.backward()

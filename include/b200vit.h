@@ -138,6 +138,21 @@ int b200vit_vq_bwd(const float* x, const float* codebook, const long long* indic
                    const float* coef, long long R, int D, int K, long long inner, long long elem_stride,
                    long long outer_stride, int flags, float* dx, float* dcodebook, void* stream);
 
+/* ---- classifier head plumbing + cross-entropy (train_vit.py:51-53,81,102; train_videogpt.py:53-54) -----------
+ * gather_token : out_bf16[B, d] = bf16(x[:, token, :]) of x[B, N, d] (fp32)  -- the operand of the head GEMM
+ * scatter_token: dx[B, N, d] (fp32) = 0 except dx[:, token] = dy[B, d] (bf16 or fp32); optional bf16 twin of dx
+ * cross_entropy_fwd: logits[R, C] (row stride ld; bf16 or fp32), labels[R] int64 -> loss[0] = mean over rows whose
+ *   label != ignore_index of (logsumexp(x) - x[label]), loss[1] = 1 / n_valid, lse[R]; row_loss[R] is scratch.
+ * cross_entropy_bwd: dlogits (dtype of the logits, row stride ldd) = (softmax(x) - onehot) * *dloss * loss[1].   */
+int b200vit_gather_token_bf16(const float* x, void* out_bf16, int B, int N, int d, int token, void* stream);
+int b200vit_scatter_token(const void* dy, int dy_is_bf16, float* dx, void* dx_bf16, int B, int N, int d, int token,
+                          void* stream);
+int b200vit_cross_entropy_fwd(const void* logits, int logits_bf16, long long ld, const long long* labels, float* loss,
+                              float* lse, float* row_loss, int R, int C, long long ignore_index, void* stream);
+int b200vit_cross_entropy_bwd(const void* logits, int logits_bf16, long long ld, const long long* labels, const float* lse,
+                              const float* loss, const float* dloss, void* dlogits, long long ldd, int R, int C,
+                              long long ignore_index, void* stream);
+
 /* ---- fused multi-tensor AdamW + bf16 operand refresh (torch.optim.AdamW at train_vit.py:82,105, ------------
  * train_titok.py:134,160, train_videogpt.py:107,134; arithmetic of torch/optim/adam.py::_single_tensor_adam)
  * tensors: device array of { float* p; const float* g; float* m; float* v; bf16* w16 (or NULL); long long n } ;

@@ -289,19 +289,25 @@ def vit_bwd(dout, cache):
     return g
 
 
-def cross_entropy_fwd(logits, labels):
+def cross_entropy_fwd(logits, labels, ignore_index=-100):
+    """nn.CrossEntropyLoss() / F.cross_entropy defaults (train_vit.py:81,102; train_videogpt.py:54): mean over the rows
+    whose label is not ignore_index of logsumexp(x) - x[label]."""
     m = logits.max(axis=-1, keepdims=True)
     lse = m + np.log(np.exp(logits - m).sum(axis=-1, keepdims=True))
     logp = logits - lse
-    loss = -logp[np.arange(logits.shape[0]), labels].mean()
-    return loss.astype(logits.dtype), (np.exp(logp), labels)
+    valid = labels != ignore_index
+    safe = np.where(valid, labels, 0)
+    rows = -logp[np.arange(logits.shape[0]), safe] * valid
+    loss = rows.sum() / valid.sum()
+    return loss.astype(logits.dtype), (np.exp(logp), labels, valid)
 
 
 def cross_entropy_bwd(cache):
-    p, labels = cache
+    p, labels, valid = cache
     d = p.copy()
-    d[np.arange(p.shape[0]), labels] -= 1.0
-    return (d / p.shape[0]).astype(p.dtype)
+    d[np.arange(p.shape[0]), np.where(valid, labels, 0)] -= 1.0
+    d *= valid[:, None]
+    return (d / valid.sum()).astype(p.dtype)
 
 
 def vit_classifier_loss_and_grads(x, labels, P, n_heads):

@@ -406,3 +406,56 @@ def test_vq_backward(ops, l2, gn, cf):
                         gather_normalized=gn, channels_first=cf)
     np.testing.assert_allclose(dx.cpu().numpy(), dx_ref, rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(dC.cpu().numpy(), dC_ref, rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ head + cross-entropy
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_cross_entropy_matches_torch_golden(ops, golden_dir, tag, dtype):
+    # golden = torch.nn.functional.cross_entropy itself (tests/golden/make_golden_ce.py), incl. ignored rows.
+    # fp32 logits: loss 1e-5 rel, d logits 1e-4 of max; bf16 logits: compared with the oracle on the SAME rounded logits
+    import os
+    g = np.load(os.path.join(golden_dir, "cross_entropy.npz"))
+    x, y = g[f"{tag}_x"], g[f"{tag}_y"]
+    if dtype == "bf16":
+        x = bf16_round(x)
+        loss_ref, cache = O.cross_entropy_fwd(x.astype(np.float64), y)
+        dx_ref = O.cross_entropy_bwd(cache)
+    else:
+        loss_ref, dx_ref = g[f"{tag}_loss"], g[f"{tag}_dx"]
+    xd = to_dev(x, torch.bfloat16 if dtype == "bf16" else None)
+    loss, lse = ops.cross_entropy_fwd(xd, to_dev(y))
+    assert abs(float(loss[0]) - float(loss_ref)) <= 1e-5 * abs(float(loss_ref)) + 1e-6
+    assert abs(float(loss[1]) - 1.0 / (y != -100).sum()) < 1e-7
+    up = torch.tensor([1.5], device=DEV)
+    dx = ops.cross_entropy_bwd(xd, to_dev(y), lse, loss, up)
+    assert dx.dtype == xd.dtype
+    assert_close_bf16(dx, dx_ref * 1.5, "d logits", rel=1e-4 if dtype == "f32" else 5e-3)
+    assert not dx.float().cpu().numpy()[y == -100].any()
+
+
+def test_cross_entropy_strided_logits_and_all_ignored(ops):
+    rng = np.random.default_rng(3)
+    full = rng.standard_normal((9, 16)).astype(np.float32)
+    y = rng.integers(0, 10, size=9).astype(np.int64)
+    xd = to_dev(full)[:, :10]   # padded head output: row stride 16, 10 classes
+    loss, lse = ops.cross_entropy_fwd(xd, to_dev(y))
+    ref, _ = O.cross_entropy_fwd(full[:, :10].astype(np.float64), y)
+    assert abs(float(loss[0]) - float(ref)) < 1e-5
+    loss, _ = ops.cross_entropy_fwd(xd, to_dev(np.full(9, -100, dtype=np.int64)))
+    assert math.isnan(float(loss[0])) and float(loss[1]) == 0.0   # torch: mean over zero rows is nan
+
+
+@pytest.mark.parametrize("B,N,d,token", [(5, 65, 192, 0), (3, 197, 768, 0), (4, 7, 64, 3)])
+def test_gather_and_scatter_token(ops, B, N, d, token):
+    rng = np.random.default_rng(B + N + d)
+    x = rng.standard_normal((B, N, d)).astype(np.float32)
+    a = ops.gather_token_bf16(to_dev(x), token)
+    assert np.array_equal(a.float().cpu().numpy(), bf16_round(np.ascontiguousarray(x[:, token])))
+    dy = bf16_round(rng.standard_normal((B, d)).astype(np.float32))
+    for dt in (torch.bfloat16, None):
+        dx, dx16 = ops.scatter_token(to_dev(dy, dt), B, N, token)
+        ref = np.zeros((B, N, d), dtype=np.float32)
+        ref[:, token] = dy
+        assert np.array_equal(dx.cpu().numpy(), ref)
+        assert np.array_equal(dx16.float().cpu().numpy(), ref)

@@ -69,7 +69,10 @@ def test_transformer_matches_reference(golden_dir, tag):
         assert torch.equal(y1, y.detach())
 
 
-def test_vit_classifier_xs_matches_reference(golden_dir):
+@pytest.mark.parametrize("fused_loss", [False, True])
+def test_vit_classifier_xs_matches_reference(golden_dir, fused_loss):
+    # fused_loss: under autocast (bf16 logits out of ClassifierHeadFn) through b200vit.CrossEntropyLoss, the way
+    # train_vit.py:100-104 runs; otherwise fp32 logits through torch's own cross entropy
     from b200vit import modules as M
     g = np.load(os.path.join(golden_dir, "vit.npz"))
     M.transformer_configs["XS"] = lambda **kw: M.TransformerConfig(n_layers=2, n_heads=1, n_embd=64, **kw)
@@ -79,8 +82,17 @@ def test_vit_classifier_xs_matches_reference(golden_dir):
     labels = torch.from_numpy(g["xs_labels"]).to(DEV)
     tokens = model.vit(x)
     assert rel_l2(tokens.detach().cpu().numpy(), g["xs_tokens"]) < 1e-2
-    logits = model(x)
-    loss = torch.nn.functional.cross_entropy(logits, labels)
+    if fused_loss:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = model(x)
+            loss = M.CrossEntropyLoss()(logits, labels)
+        assert logits.dtype == torch.bfloat16 and loss.dtype == torch.float32
+    else:
+        logits = model(x)
+        assert logits.dtype == torch.float32
+        loss = torch.nn.functional.cross_entropy(logits, labels)
+    assert logits.shape == (x.shape[0], 10)
+    assert rel_l2(logits.detach().float().cpu().numpy(), g["xs_logits"]) < 2e-2
     assert abs(loss.item() - float(g["xs_loss"])) < 2e-2 * abs(float(g["xs_loss"]))
     loss.backward()
     for k, p in model.named_parameters():

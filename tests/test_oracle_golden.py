@@ -211,3 +211,12 @@ def test_adamw_oracle(golden_dir):
     pa, ma, va, _ = A.adamw_step(p0, g0 * np.float32(1024.0), z, z, 1, 1e-3, grad_scale=1024.0)
     pb, mb, vb, _ = A.adamw_step(p0, g0, z, z, 1, 1e-3)
     np.testing.assert_allclose(pa, pb, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_cross_entropy_oracle(golden_dir, tag):
+    """oracle cross-entropy (with ignore_index) against torch.nn.functional.cross_entropy (tests/golden/make_golden_ce.py)."""
+    g = _load(golden_dir, "cross_entropy.npz")
+    loss, cache = O.cross_entropy_fwd(g[f"{tag}_x"], g[f"{tag}_y"])
+    np.testing.assert_allclose(loss, g[f"{tag}_loss"], rtol=1e-5)
+    np.testing.assert_allclose(O.cross_entropy_bwd(cache), g[f"{tag}_dx"], rtol=1e-4, atol=1e-7)

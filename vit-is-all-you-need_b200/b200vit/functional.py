@@ -205,7 +205,10 @@ class TransformerStackFn(torch.autograd.Function):
     def backward(ctx, dy):
         B, N, d, H, causal = ctx.dims
         dx = _as_rows_f32(dy).view(B * N, d)
+        twin = getattr(dy, "_b200_bf16_twin", None)   # ClassifierHeadFn.backward hands the bf16 copy along
         dx_bf16 = None
+        if twin is not None and twin[1] == dy._version and dy.dtype == F32 and dy.is_contiguous() and twin[0].shape == dy.shape:
+            dx_bf16 = twin[0].view(B * N, d)
         grads = []
         n = len(ctx.layers)
         for i in range(n - 1, -1, -1):
@@ -309,6 +312,83 @@ class PatchConvFn(torch.autograd.Function):
             dcols = ops.gemm_dgrad(dy2, bf16_of(weight).view(d, -1))
             dx = ops.col2im(dcols, B, C, H, W, p)
         return dx, dW.view(weight.shape), (db if ctx.has_bias else None), None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Classifier head and loss: head(vit(x)[:, 0]) (train_vit.py:51-53), nn.CrossEntropyLoss (train_vit.py:81,102)
+# ------------------------------------------------------------------------------------------------------------
+def _pad_rows(t, rows):
+    if t is None or t.shape[0] == rows:
+        return t
+    out = t.new_zeros((rows,) + tuple(t.shape[1:]))
+    out[: t.shape[0]] = t
+    return out
+
+
+class ClassifierHeadFn(torch.autograd.Function):
+    """logits = x[:, token] @ W^T + b.  The token rows are gathered straight into the bf16 GEMM operand; backward writes
+    the [B, N, d] gradient (zero except that token) and its bf16 twin in one pass of stores.  The class count is padded
+    to a multiple of 8 inside (TMA row pitch), e.g. the 10 classes of BASELINE configs[0]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, token, out_bf16):
+        B, N, d = x.shape
+        C = weight.shape[0]
+        Cp = (C + 7) // 8 * 8
+        a = ops.gather_token_bf16(_as_rows_f32(x), token)
+        w16 = _pad_rows(bf16_of(weight), Cp)
+        b32 = _pad_rows(_f32c(bias), Cp)
+        y = ops.gemm_bias(a, w16, b32) if out_bf16 else ops.gemm_bias_f32(a, w16, b32)
+        ctx.saved = (a, w16, weight)
+        ctx.dims = (B, N, d, C, Cp, token)
+        ctx.has_bias = bias is not None
+        ctx.x_needs_grad = x.requires_grad
+        return y[:, :C] if Cp != C else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, w16, weight = ctx.saved
+        B, N, d, C, Cp, token = ctx.dims
+        dy16 = dy.to(BF16)
+        if Cp != C:
+            dy16 = torch.nn.functional.pad(dy16, (0, Cp - C))
+        dy16 = dy16.contiguous()
+        dW, db = ops.gemm_wgrad(dy16, a, want_bias=True)
+        dx = None
+        if ctx.x_needs_grad:
+            da = ops.gemm_dgrad(dy16, w16)
+            dx, dx16 = ops.scatter_token(da, B, N, token, want_bf16=True)
+            # TransformerStackFn.backward picks the twin up instead of re-casting 155 MB; the version guards against
+            # autograd accumulating another gradient into dx in place on the way there
+            dx._b200_bf16_twin = (dx16, dx._version)
+        ctx.saved = None
+        return dx, dW[:C], (db[:C] if ctx.has_bias else None), None, None
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """F.cross_entropy(logits, labels) with reduction='mean' and ignore_index (train_vit.py:81,102, train_videogpt.py:54)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        C = logits.shape[-1]
+        x2 = logits.reshape(-1, C)
+        if x2.dtype not in (BF16, F32):
+            x2 = x2.float()
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        y = labels.reshape(-1).contiguous()
+        loss, lse = ops.cross_entropy_fwd(x2, y, ignore_index)
+        ctx.saved = (x2, y, lse, loss)
+        ctx.meta = (logits.shape, logits.dtype, ignore_index)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        x2, y, lse, loss = ctx.saved
+        shape, dtype, ignore_index = ctx.meta
+        d = ops.cross_entropy_bwd(x2, y, lse, loss, dloss.detach().float().reshape(1).contiguous(), ignore_index)
+        ctx.saved = None
+        return d.to(dtype).view(shape), None, None
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ What it does:
     through the im2col + tcgen05 GEMM path and is otherwise nn.Conv2d;
   * torch.optim.AdamW becomes b200vit.optim.AdamW (one fused multi-tensor launch that also refreshes the bf16 GEMM operands;
     same constructor, state_dict layout and GradScaler protocol; B200VIT_TORCH_ADAMW=1 keeps torch's);
+  * F.cross_entropy (and with it nn.CrossEntropyLoss) takes the fused cross-entropy kernels for 2-D CUDA logits;
   * stubs two imports the scripts never use (lpips, vector_quantize_pytorch.FSQ) when they are not installed,
     disables wandb, and (B200VIT_SYNTHETIC=1) replaces the hard-coded ImageNet loaders with synthetic ones.
 """
@@ -89,6 +90,29 @@ def install_optimizer_swap():
     return orig
 
 
+def install_loss_swap():
+    """nn.CrossEntropyLoss (train_vit.py:81) and F.cross_entropy (train_videogpt.py:54) -> the fused kernels of
+    csrc/head_ce.cu for what those call sites pass (2-D CUDA logits, int64 labels, default arguments); any other use keeps
+    torch's implementation, like PatchConv2d does for non-patchify convolutions."""
+    import torch
+    import torch.nn.functional as F
+
+    from . import functional as Fn
+    orig_fn = F.cross_entropy
+
+    def cross_entropy(input, target, weight=None, size_average=None, ignore_index=-100, reduce=None, reduction="mean",
+                      label_smoothing=0.0):
+        if (input.is_cuda and input.dim() == 2 and target.dtype == torch.int64 and target.dim() == 1 and weight is None
+                and size_average is None and reduce is None and reduction == "mean" and label_smoothing == 0.0
+                and input.dtype in (torch.float32, torch.bfloat16)):
+            return Fn.CrossEntropyFn.apply(input, target, ignore_index)
+        return orig_fn(input, target, weight=weight, size_average=size_average, ignore_index=ignore_index, reduce=reduce,
+                       reduction=reduction, label_smoothing=label_smoothing)
+
+    F.cross_entropy = cross_entropy   # nn.CrossEntropyLoss.forward calls F.cross_entropy, so both entry points are covered
+    return orig_fn
+
+
 def install_synthetic_loaders():
     """datasets.get_imagenet_loaders has a hard-coded dataset root (datasets.py:7,23); benchmarks and smoke runs
     use synthetic tensors of the same shapes instead."""
@@ -126,6 +150,7 @@ def main(argv=None):
     install_conv_swap()
     if os.environ.get("B200VIT_TORCH_ADAMW", "0") != "1":
         install_optimizer_swap()
+    install_loss_swap()
     sys.argv = [script] + argv[1:]
     try:
         runpy.run_path(script, run_name="__main__")

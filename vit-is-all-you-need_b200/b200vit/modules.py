@@ -156,7 +156,9 @@ class ViT(nn.Module):
 
 
 class ViTClassifier(nn.Module):
-    """train_vit.ViTClassifier (train_vit.py:47-53); the head stays a plain nn.Linear (SURVEY.md §8f "next")."""
+    """train_vit.ViTClassifier (train_vit.py:47-53): head(vit(x)[:, 0]).  `head` is an ordinary nn.Linear parameter
+    container (same state_dict keys); the token gather, the tcgen05 GEMM and the backward scatter run in ClassifierHeadFn.
+    Like nn.Linear under autocast the logits are bf16 when autocast is on and fp32 otherwise."""
 
     def __init__(self, vit_config: ViTConfig, num_classes=1000):
         super().__init__()
@@ -164,7 +166,27 @@ class ViTClassifier(nn.Module):
         self.head = nn.Linear(vit_config.trans_config.n_embd, num_classes)
 
     def forward(self, x):
-        return self.head(self.vit(x)[:, 0])
+        return Fn.ClassifierHeadFn.apply(self.vit(x), self.head.weight, self.head.bias, 0, torch.is_autocast_enabled())
+
+
+class CrossEntropyLoss(nn.Module):
+    """nn.CrossEntropyLoss() as the reference scripts build it (train_vit.py:81, mean reduction, no class weights, no label
+    smoothing) over the fused kernels of csrc/head_ce.cu; logits [R, C] in bf16 or fp32, int64 class labels [R].
+    b200vit.launch installs it as torch.nn.CrossEntropyLoss; other configurations raise rather than fall back."""
+
+    def __init__(self, weight=None, size_average=None, ignore_index=-100, reduce=None, reduction="mean", label_smoothing=0.0):
+        super().__init__()
+        if weight is not None or reduction != "mean" or label_smoothing != 0.0 or size_average is not None or reduce is not None:
+            raise NotImplementedError("b200vit.CrossEntropyLoss implements reduction='mean' without class weights or label "
+                                      "smoothing (what the reference scripts use)")
+        self.ignore_index = ignore_index
+        self.reduction = reduction
+
+    def forward(self, input, target):
+        if input.dim() != 2 or target.dtype != torch.int64 or target.shape != input.shape[:1]:
+            raise NotImplementedError("b200vit.CrossEntropyLoss takes logits [R, C] and int64 class indices [R] "
+                                      "(train_vit.py:102, train_videogpt.py:54)")
+        return Fn.CrossEntropyFn.apply(input, target, self.ignore_index)
 
 
 class PatchConv2d(nn.Conv2d):

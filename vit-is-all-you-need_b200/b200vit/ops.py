@@ -19,7 +19,7 @@ launch_count = 0  # number of C-ABI compute calls issued (bench.py reports it as
 
 
 # kernels launched per C-ABI call (memsets not counted); everything else launches exactly one kernel
-_KERNELS_PER_CALL = {"b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3}
+_KERNELS_PER_CALL = {"b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3, "b200vit_cross_entropy_fwd": 2}
 
 _prof = None  # list of (start_event, end_event, flops) while profile_gemms() is active
 
@@ -272,6 +272,49 @@ def cast_bf16(t, out=None):
     else:
         out.copy_(t)
     return out
+
+
+# ---------------------------------------------------------------- classifier head + cross-entropy
+def gather_token_bf16(x, token=0):
+    """x [B, N, d] fp32 -> bf16 [B, d] rows of one token (the operand of the head GEMM, train_vit.py:53)."""
+    B, N, d = x.shape
+    out = torch.empty(B, d, device=x.device, dtype=BF16)
+    _call("b200vit_gather_token_bf16", x, ptr(_chk(x, F32, "x")), ptr(out), B, N, d, token, stream_ptr())
+    return out
+
+
+def scatter_token(dy, B, N, token=0, want_bf16=True):
+    """Gradient of x[:, token]: fp32 [B, N, d] that is zero except for that token's rows, plus its bf16 twin."""
+    d = dy.shape[-1]
+    if dy.dtype not in (BF16, F32) or not dy.is_contiguous():
+        raise TypeError("scatter_token: dy must be a contiguous bf16 or fp32 tensor")
+    dx = torch.empty(B, N, d, device=dy.device, dtype=F32)
+    dxb = torch.empty(B, N, d, device=dy.device, dtype=BF16) if want_bf16 else None
+    _call("b200vit_scatter_token", dy, ptr(dy), 1 if dy.dtype == BF16 else 0, ptr(dx), ptr(dxb), B, N, d, token, stream_ptr(),
+          hbm_bytes=float(B * N * d * (4 + (2 if want_bf16 else 0))))
+    return dx, dxb
+
+
+def cross_entropy_fwd(logits, labels, ignore_index=-100):
+    """logits [R, C] (bf16 or fp32, last dim contiguous), labels [R] int64 -> (loss2 = [mean loss, 1/n_valid], lse [R])."""
+    R, C = logits.shape
+    if logits.dtype not in (BF16, F32) or logits.stride(1) != 1:
+        raise TypeError("cross_entropy_fwd: logits must be bf16 or fp32 with a contiguous class dimension")
+    labels = _chk(labels, torch.int64, "labels")
+    loss = torch.empty(2, device=logits.device, dtype=F32)
+    lse = torch.empty(R, device=logits.device, dtype=F32)
+    scratch = torch.empty(R, device=logits.device, dtype=F32)
+    _call("b200vit_cross_entropy_fwd", logits, ptr(logits), 1 if logits.dtype == BF16 else 0, logits.stride(0), ptr(labels),
+          ptr(loss), ptr(lse), ptr(scratch), R, C, ignore_index, stream_ptr())
+    return loss, lse
+
+
+def cross_entropy_bwd(logits, labels, lse, loss, dloss, ignore_index=-100):
+    R, C = logits.shape
+    dlogits = torch.empty(R, C, device=logits.device, dtype=logits.dtype)
+    _call("b200vit_cross_entropy_bwd", logits, ptr(logits), 1 if logits.dtype == BF16 else 0, logits.stride(0), ptr(labels),
+          ptr(lse), ptr(loss), ptr(_chk(dloss, F32, "dloss")), ptr(dlogits), C, R, C, ignore_index, stream_ptr())
+    return dlogits
 
 
 # ---------------------------------------------------------------- patch embedding

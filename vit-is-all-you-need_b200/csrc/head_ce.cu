@@ -71,12 +71,6 @@ template <typename T> __device__ __forceinline__ void st_logit(T* p, float v);
 template <> __device__ __forceinline__ void st_logit<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void st_logit<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
 constexpr int CE_WARPS = 8;
 
 // one warp per row: max, sum of exponentials (second read hits L1/L2), row loss
@@ -92,7 +86,7 @@ ce_fwd_kernel(const T* __restrict__ logits, long long ld, const long long* __res
   for (int c = lane; c < C; c += 32) mx = fmaxf(mx, ld_logit<T>(x + c));
   mx = warp_max(mx);
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += __expf(ld_logit<T>(x + c) - mx);
+  for (int c = lane; c < C; c += 32) s += expf(ld_logit<T>(x + c) - mx);
   s = warp_sum(s);
   if (lane == 0) {
     const float l = mx + logf(s);
@@ -139,7 +133,7 @@ ce_bwd_kernel(const T* __restrict__ logits, long long ld, const long long* __res
   const T* x = logits + r * ld;
   T* dx = dlogits + r * ldd;
   for (int c = lane; c < C; c += 32) {
-    const float p = __expf(ld_logit<T>(x + c) - l);
+    const float p = expf(ld_logit<T>(x + c) - l);
     st_logit<T>(dx + c, (p - (c == y ? 1.f : 0.f)) * scale);
   }
 }
