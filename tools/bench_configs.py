@@ -41,14 +41,15 @@ M.transformer_configs.setdefault("Ti", lambda **kw: M.TransformerConfig(12, 3, 1
 def vit_step(name, size, patch, model, B, classes):
     torch.manual_seed(0)
     net = M.ViTClassifier(M.ViTConfig(size, 3, patch, model, 1, 0.0), num_classes=classes).to(dev)
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, fused=True)
+    from b200vit.optim import AdamW
+    opt = AdamW(net.parameters(), lr=1e-4)
     x = torch.randn(B, 3, size, size, device=dev)
     y = torch.randint(0, classes, (B,), device=dev)
 
     def step():
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss = torch.nn.functional.cross_entropy(net(x).float(), y)
+            loss = M.CrossEntropyLoss()(net(x), y)
         loss.backward()
         opt.step()
     ms = timeit(step)

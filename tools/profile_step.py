@@ -22,7 +22,8 @@ args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = M.ViTClassifier(M.ViTConfig(224, 3, 16, args.model, 1, 0.0), num_classes=1000).to(dev)
-optim = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2, fused=True)
+from b200vit.optim import AdamW  # noqa: E402
+optim = AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2)
 x = torch.randn(args.batch, 3, 224, 224, device=dev)
 y = torch.randint(0, 1000, (args.batch,), device=dev)
 
@@ -30,7 +31,7 @@ y = torch.randint(0, 1000, (args.batch,), device=dev)
 def step():
     optim.zero_grad(set_to_none=True)
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        loss = torch.nn.functional.cross_entropy(model(x).float(), y)
+        loss = M.CrossEntropyLoss()(model(x), y)
     loss.backward()
     optim.step()
     return loss

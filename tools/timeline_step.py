@@ -41,7 +41,8 @@ if world > 1:  # torchrun: the same step through the data-parallel wrapper (rank
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
     net = ddp.DataParallel(model)
-optim = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2, fused=True)
+from b200vit.optim import AdamW  # noqa: E402
+optim = AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2)
 x = torch.randn(args.batch, 3, 224, 224, device=dev)
 y = torch.randint(0, 1000, (args.batch,), device=dev)
 
@@ -49,7 +50,7 @@ y = torch.randint(0, 1000, (args.batch,), device=dev)
 def step():
     optim.zero_grad(set_to_none=True)
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        loss = torch.nn.functional.cross_entropy(net(x).float(), y)
+        loss = M.CrossEntropyLoss()(net(x), y)
     loss.backward()
     optim.step()
     return loss
