@@ -120,6 +120,13 @@ int b200vit_patch_embed_fwd(const float* x, const void* w_bf16, const float* bia
 /* dsum[T, d] = sum_b dtokens[b] ; dpe_bf16[B*P, d] = bf16(dtokens[:, extra:])                                */
 int b200vit_patch_embed_bwd_reduce(const float* dtokens, float* dsum, void* dpe_bf16, int B, int T, int extra,
                                    int d, void* stream);
+/* de-patchify tail of the tokenizer decoders (train_titok.py:67,72-74): 1x1 Conv2d(d -> C*p*p) over the patch tokens +
+ * "b (p1 p2 c) h w -> b c (h p1) (w p2)" as ONE GEMM whose epilogue stores straight into the NCHW image.
+ * rows_bf16[B*P, d]; w_cmajor_bf16[C*p*p, d] and bias_cmajor[C*p*p] hold the conv's output channels re-ordered from the
+ * reference's (p1 p2 c) to (c p1 p2); img[B, C, Ht*p, Wt*p] fp32; p a power of two >= 4.  Backward: im2col_bf16 of the
+ * image gradient yields exactly the (c p1 p2)-ordered rows for the wgrad / dgrad GEMMs.                        */
+int b200vit_depatchify_fwd(const void* rows_bf16, const void* w_cmajor_bf16, const float* bias_cmajor, float* img, int B,
+                           int Ht, int Wt, int p, int C, int d, void* stream);
 int b200vit_im2col_bf16(const float* x, void* cols, int B, int C, int H, int W, int p, void* stream);
 int b200vit_col2im_f32(const void* dcols, float* dx, int B, int C, int H, int W, int p, void* stream);
 
@@ -139,14 +146,15 @@ int b200vit_vq_bwd(const float* x, const float* codebook, const long long* indic
                    long long outer_stride, int flags, float* dx, float* dcodebook, void* stream);
 
 /* ---- classifier head plumbing + cross-entropy (train_vit.py:51-53,81,102; train_videogpt.py:53-54) -----------
- * gather_token : out_bf16[B, d] = bf16(x[:, token, :]) of x[B, N, d] (fp32)  -- the operand of the head GEMM
- * scatter_token: dx[B, N, d] (fp32) = 0 except dx[:, token] = dy[B, d] (bf16 or fp32); optional bf16 twin of dx
+ * gather_tokens : out_bf16[B*cnt, d] = bf16(x[:, t0:t0+cnt, :]) of x[B, N, d] (fp32) -- the operand of the head GEMM
+ *   (cnt = 1), of TiTokEncoder.proj (train_titok.py:41-42) and of the de-patchify GEMM (train_titok.py:71)
+ * scatter_tokens: dx[B, N, d] (fp32) = 0 except dx[:, t0:t0+cnt] = dy[B*cnt, d] (bf16 or fp32); optional bf16 twin
  * cross_entropy_fwd: logits[R, C] (row stride ld; bf16 or fp32), labels[R] int64 -> loss[0] = mean over rows whose
  *   label != ignore_index of (logsumexp(x) - x[label]), loss[1] = 1 / n_valid, lse[R]; row_loss[R] is scratch.
  * cross_entropy_bwd: dlogits (dtype of the logits, row stride ldd) = (softmax(x) - onehot) * *dloss * loss[1].   */
-int b200vit_gather_token_bf16(const float* x, void* out_bf16, int B, int N, int d, int token, void* stream);
-int b200vit_scatter_token(const void* dy, int dy_is_bf16, float* dx, void* dx_bf16, int B, int N, int d, int token,
-                          void* stream);
+int b200vit_gather_tokens_bf16(const float* x, void* out_bf16, int B, int N, int d, int t0, int cnt, void* stream);
+int b200vit_scatter_tokens(const void* dy, int dy_is_bf16, float* dx, void* dx_bf16, int B, int N, int d, int t0, int cnt,
+                           void* stream);
 int b200vit_cross_entropy_fwd(const void* logits, int logits_bf16, long long ld, const long long* labels, float* loss,
                               float* lse, float* row_loss, int R, int C, long long ignore_index, void* stream);
 int b200vit_cross_entropy_bwd(const void* logits, int logits_bf16, long long ld, const long long* labels, const float* lse,

@@ -446,16 +446,32 @@ def test_cross_entropy_strided_logits_and_all_ignored(ops):
     assert math.isnan(float(loss[0])) and float(loss[1]) == 0.0   # torch: mean over zero rows is nan
 
 
-@pytest.mark.parametrize("B,N,d,token", [(5, 65, 192, 0), (3, 197, 768, 0), (4, 7, 64, 3)])
-def test_gather_and_scatter_token(ops, B, N, d, token):
-    rng = np.random.default_rng(B + N + d)
+@pytest.mark.parametrize("B,N,d,t0,cnt", [(5, 65, 192, 0, 1), (3, 197, 768, 0, 1), (4, 7, 64, 3, 1), (3, 288, 512, 0, 32),
+                                         (2, 288, 512, 0, 256), (2, 40, 64, 5, 7)])
+def test_gather_and_scatter_tokens(ops, B, N, d, t0, cnt):
+    rng = np.random.default_rng(B + N + d + cnt)
     x = rng.standard_normal((B, N, d)).astype(np.float32)
-    a = ops.gather_token_bf16(to_dev(x), token)
-    assert np.array_equal(a.float().cpu().numpy(), bf16_round(np.ascontiguousarray(x[:, token])))
-    dy = bf16_round(rng.standard_normal((B, d)).astype(np.float32))
+    a = ops.gather_tokens_bf16(to_dev(x), t0, cnt)
+    assert np.array_equal(a.float().cpu().numpy(), bf16_round(np.ascontiguousarray(x[:, t0:t0 + cnt])).reshape(B * cnt, d))
+    dy = bf16_round(rng.standard_normal((B * cnt, d)).astype(np.float32))
     for dt in (torch.bfloat16, None):
-        dx, dx16 = ops.scatter_token(to_dev(dy, dt), B, N, token)
+        dx, dx16 = ops.scatter_tokens(to_dev(dy, dt), B, N, t0, cnt)
         ref = np.zeros((B, N, d), dtype=np.float32)
-        ref[:, token] = dy
+        ref[:, t0:t0 + cnt] = dy.reshape(B, cnt, d)
         assert np.array_equal(dx.cpu().numpy(), ref)
         assert np.array_equal(dx16.float().cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("B,Ht,Wt,p,C,d", [(3, 16, 16, 16, 3, 512), (2, 8, 8, 8, 3, 768), (5, 4, 6, 4, 3, 64), (1, 2, 2, 16, 1, 128)])
+def test_depatchify_gemm_epilogue(ops, B, Ht, Wt, p, C, d):
+    # train_titok.py:67,72-74: Conv2d(d, C*p*p, 1) over the patch tokens + 'b (p1 p2 c) h w -> b c (h p1) (w p2)'
+    rng = np.random.default_rng(B + Ht + p + d)
+    rows = bf16_round(rng.standard_normal((B * Ht * Wt, d)).astype(np.float32))
+    w_ref = bf16_round((rng.standard_normal((C * p * p, d)) * 0.05).astype(np.float32))   # reference order (p1 p2 c)
+    b_ref = (rng.standard_normal(C * p * p) * 0.1).astype(np.float32)
+    y = rows.astype(np.float64) @ w_ref.astype(np.float64).T + b_ref                      # [B*P, (p1 p2 c)]
+    img_ref = y.reshape(B, Ht, Wt, p, p, C).transpose(0, 5, 1, 3, 2, 4).reshape(B, C, Ht * p, Wt * p)
+    perm = np.arange(C * p * p).reshape(p, p, C).transpose(2, 0, 1).reshape(-1)           # (c p1 p2) -> index in (p1 p2 c)
+    img = ops.depatchify_fwd(to_dev(rows, torch.bfloat16), to_dev(w_ref[perm], torch.bfloat16), to_dev(b_ref[perm]), B, Ht, Wt, p, C)
+    assert img.shape == (B, C, Ht * p, Wt * p)
+    assert_close_bf16(img, img_ref, "de-patchified image", rel=2e-5)

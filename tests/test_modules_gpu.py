@@ -253,3 +253,93 @@ def test_transformer_dropout_semantics():
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+# ------------------------------------------------------------------------------------------------ TiTok encoder / decoder
+def _det_weights_like_golden(module, seed, scale=0.05):
+    """tests/golden/make_golden.py:det_weights: numpy Generator values in state_dict order."""
+    rng = np.random.default_rng(seed)
+    new = {}
+    for k, v in module.state_dict().items():
+        a = rng.standard_normal(tuple(v.shape)).astype(np.float32) * scale
+        new[k] = torch.from_numpy(a)
+    module.load_state_dict(new)
+    return module
+
+
+class _TiTokCfg:
+    """train_titok.TiTokConfig (train_titok.py:18-32) for the miniature fixture."""
+
+    def __init__(self, M, image_size, patch_size, latent_tokens, codebook_size, latent_dim, transformer):
+        self.image_size, self.patch_size, self.latent_tokens = image_size, patch_size, latent_tokens
+        self.codebook_size, self.latent_dim, self.transformer = codebook_size, latent_dim, transformer
+        self.patch_dim = image_size // patch_size
+        self.n_patches = self.patch_dim ** 2
+        self.enc_vit_config = M.ViTConfig(image_size, 3, patch_size, transformer, latent_tokens, 0.0)
+        self.n_embd = self.enc_vit_config.trans_config.n_embd
+        self.dec_vit_config = M.ViTConfig(latent_tokens, self.n_embd, 1, transformer, self.n_patches, 0.0)
+        self.dec_vit_config.n_patches = latent_tokens
+
+
+def _check_titok_grads(model, g, prefix):
+    for k, p in model.named_parameters():
+        got = p.grad.detach().float().cpu().numpy()
+        if f"{prefix}_g_{k}" in g.files:
+            check_grad(p.grad, g[f"{prefix}_g_{k}"], f"{prefix} {k}", tol=3e-2)
+        else:
+            norm = float(g[f"{prefix}_gn_{k}"])
+            assert abs(np.linalg.norm(got.astype(np.float64)) - norm) < 3e-2 * norm + 1e-7, f"{prefix} {k} norm"
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_titok_encoder_matches_reference(golden_dir, autocast):
+    from b200vit import modules as M
+    g = np.load(os.path.join(golden_dir, "titok.npz"))
+    M.transformer_configs["XS"] = lambda **kw: M.TransformerConfig(n_layers=2, n_heads=1, n_embd=64, **kw)
+    cfg = _TiTokCfg(M, *(int(v) for v in g["cfg"]), "XS")
+    enc = M.TiTokEncoder(cfg)
+    assert list(enc.state_dict().keys()) == [str(k) for k in g["enc_keys"]]
+    enc = _det_weights_like_golden(enc, seed=41).to(DEV)
+    x = torch.from_numpy(g["enc_x"]).to(DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        lat = enc(x)
+    assert lat.shape == (3, 8, 12) and lat.dtype == (torch.bfloat16 if autocast else torch.float32)
+    assert rel_l2(lat.detach().float().cpu().numpy(), g["enc_lat"]) < 1.5e-2
+    lat.backward(torch.from_numpy(g["enc_dlat"]).to(DEV).to(lat.dtype))
+    _check_titok_grads(enc, g, "enc")
+
+
+def test_titok_decoder_matches_reference(golden_dir):
+    from b200vit import modules as M
+    g = np.load(os.path.join(golden_dir, "titok.npz"))
+    M.transformer_configs["XS"] = lambda **kw: M.TransformerConfig(n_layers=2, n_heads=1, n_embd=64, **kw)
+    cfg = _TiTokCfg(M, *(int(v) for v in g["cfg"]), "XS")
+    dec = M.TiTokDecoder(cfg)
+    assert list(dec.state_dict().keys()) == [str(k) for k in g["dec_keys"]]
+    dec = _det_weights_like_golden(dec, seed=42).to(DEV)
+    z = torch.from_numpy(g["dec_z"]).to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        img = dec(z)
+    assert img.shape == (3, 3, 32, 32) and img.dtype == torch.float32
+    assert rel_l2(img.detach().cpu().numpy(), g["dec_img"]) < 1.5e-2
+    img.backward(torch.from_numpy(g["dec_dimg"]).to(DEV))
+    check_grad(z.grad, g["dec_dz"], "d z", tol=3e-2)
+    _check_titok_grads(dec, g, "dec")
+
+
+def test_titok_full_model_runs_and_matches_shapes():
+    """train_titok.TiTok.forward (train_titok.py:87-91) end to end on the drop-ins: shapes, dtypes, finite gradients everywhere."""
+    from b200vit import modules as M
+    M.transformer_configs["XS"] = lambda **kw: M.TransformerConfig(n_layers=2, n_heads=1, n_embd=64, **kw)
+    cfg = _TiTokCfg(M, 32, 4, 8, 64, 12, "XS")
+    torch.manual_seed(0)
+    model = M.TiTok(cfg).to(DEV)
+    x = torch.rand(4, 3, 32, 32, device=DEV)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        recon, idx, qloss = model(x)
+        loss = (recon - x).pow(2).mean() + qloss
+    assert recon.shape == x.shape and idx.shape == (4, 8) and idx.dtype == torch.int64
+    loss.backward()
+    for k, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    assert model.decode_indices(idx).shape == recon.shape

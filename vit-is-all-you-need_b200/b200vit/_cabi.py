@@ -68,8 +68,9 @@ _SIGNATURES = {
     "b200vit_patch_embed_bwd_reduce": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "b200vit_im2col_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "b200vit_col2im_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
-    "b200vit_gather_token_bf16": (_I, [_P, _P, _I, _I, _I, _I, _P]),
-    "b200vit_scatter_token": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "b200vit_gather_tokens_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200vit_scatter_tokens": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200vit_depatchify_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "b200vit_cross_entropy_fwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _I, _I, _L, _P]),
     "b200vit_cross_entropy_bwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _L, _I, _I, _L, _P]),
     "b200vit_adamw_chunk_elems": (_I, []),

@@ -325,22 +325,29 @@ def _pad_rows(t, rows):
     return out
 
 
-class ClassifierHeadFn(torch.autograd.Function):
-    """logits = x[:, token] @ W^T + b.  The token rows are gathered straight into the bf16 GEMM operand; backward writes
-    the [B, N, d] gradient (zero except that token) and its bf16 twin in one pass of stores.  The class count is padded
-    to a multiple of 8 inside (TMA row pitch), e.g. the 10 classes of BASELINE configs[0]."""
+def _pad_cols(t, cols):
+    if t.shape[-1] == cols:
+        return t
+    return torch.nn.functional.pad(t, (0, cols - t.shape[-1]))
+
+
+class TokenLinearFn(torch.autograd.Function):
+    """y[B*cnt, C] = x[:, t0:t0+cnt] @ W^T + b for x [B, N, d] fp32: the classifier head on token 0 (train_vit.py:53) and
+    TiTokEncoder.proj on the latent tokens (train_titok.py:41-42).  The token rows are gathered straight into the bf16
+    GEMM operand; backward writes the [B, N, d] gradient (zero outside those tokens) and its bf16 twin in one pass of
+    stores.  The output width is padded to a multiple of 8 inside (TMA row pitch): 10 classes, 12 latent dims."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, token, out_bf16):
+    def forward(ctx, x, weight, bias, t0, cnt, out_bf16):
         B, N, d = x.shape
         C = weight.shape[0]
         Cp = (C + 7) // 8 * 8
-        a = ops.gather_token_bf16(_as_rows_f32(x), token)
+        a = ops.gather_tokens_bf16(_as_rows_f32(x), t0, cnt)
         w16 = _pad_rows(bf16_of(weight), Cp)
         b32 = _pad_rows(_f32c(bias), Cp)
         y = ops.gemm_bias(a, w16, b32) if out_bf16 else ops.gemm_bias_f32(a, w16, b32)
         ctx.saved = (a, w16, weight)
-        ctx.dims = (B, N, d, C, Cp, token)
+        ctx.dims = (B, N, d, C, Cp, t0, cnt)
         ctx.has_bias = bias is not None
         ctx.x_needs_grad = x.requires_grad
         return y[:, :C] if Cp != C else y
@@ -348,21 +355,103 @@ class ClassifierHeadFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         a, w16, weight = ctx.saved
-        B, N, d, C, Cp, token = ctx.dims
-        dy16 = dy.to(BF16)
-        if Cp != C:
-            dy16 = torch.nn.functional.pad(dy16, (0, Cp - C))
-        dy16 = dy16.contiguous()
+        B, N, d, C, Cp, t0, cnt = ctx.dims
+        dy16 = _pad_cols(dy.to(BF16), Cp).contiguous()
         dW, db = ops.gemm_wgrad(dy16, a, want_bias=True)
         dx = None
         if ctx.x_needs_grad:
             da = ops.gemm_dgrad(dy16, w16)
-            dx, dx16 = ops.scatter_token(da, B, N, token, want_bf16=True)
+            dx, dx16 = ops.scatter_tokens(da, B, N, t0, cnt, want_bf16=True)
             # TransformerStackFn.backward picks the twin up instead of re-casting 155 MB; the version guards against
             # autograd accumulating another gradient into dx in place on the way there
             dx._b200_bf16_twin = (dx16, dx._version)
         ctx.saved = None
-        return dx, dW[:C], (db[:C] if ctx.has_bias else None), None, None
+        return dx, dW[:C], (db[:C] if ctx.has_bias else None), None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on rows [M, K] through the tcgen05 GEMMs, for the skinny projections either side of the quantiser
+    (TiTokDecoder.quant_proj 12 -> d, train_titok.py:66,70).  K and N are zero-padded to multiples of 8 inside."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, out_bf16):
+        K, N = weight.shape[1], weight.shape[0]
+        Kp, Np = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+        x2 = x.reshape(-1, K)
+        a = _pad_cols(x2.detach().to(BF16), Kp).contiguous()
+        w16 = _pad_rows(_pad_cols(bf16_of(weight), Kp), Np).contiguous()
+        b32 = _pad_rows(_f32c(bias), Np)
+        y = ops.gemm_bias(a, w16, b32) if out_bf16 else ops.gemm_bias_f32(a, w16, b32)
+        ctx.saved = (a, w16)
+        ctx.dims = (tuple(x.shape), x.dtype, K, N, Kp, Np)
+        ctx.has_bias = bias is not None
+        ctx.x_needs_grad = x.requires_grad
+        return (y[:, :N] if Np != N else y).reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, w16 = ctx.saved
+        xshape, xdtype, K, N, Kp, Np = ctx.dims
+        dy16 = _pad_cols(dy.reshape(-1, N).to(BF16), Np).contiguous()
+        dW, db = ops.gemm_wgrad(dy16, a, want_bias=True)
+        dx = None
+        if ctx.x_needs_grad:
+            dx = ops.gemm_dgrad(dy16, w16)[:, :K].to(xdtype).reshape(xshape)
+        ctx.saved = None
+        return dx, dW[:N, :K], (db[:N] if ctx.has_bias else None), None
+
+
+_DEPATCH_PERM = {}
+
+
+def _depatch_perm(C, p, device):
+    """index of output channel (c p1 p2) in the reference's (p1 p2 c) order (train_titok.py:74) and its inverse."""
+    key = (C, p, str(device))
+    if key not in _DEPATCH_PERM:
+        perm = torch.arange(C * p * p).view(p, p, C).permute(2, 0, 1).reshape(-1)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(C * p * p)
+        _DEPATCH_PERM[key] = (perm.to(device), inv.to(device))
+    return _DEPATCH_PERM[key]
+
+
+class DepatchifyFn(torch.autograd.Function):
+    """De-patchify tail of the tokenizer decoders (train_titok.py:67,71-74): tokens[:, :P] -> 'b (h w) c -> b c h w' ->
+    Conv2d(d, C*p*p, 1) -> 'b (p1 p2 c) h w -> b c (h p1) (w p2)', as ONE tcgen05 GEMM over the gathered bf16 token rows
+    whose epilogue stores straight into the NCHW fp32 image (the conv's output channels are re-ordered to (c p1 p2) so that
+    a thread's consecutive accumulator columns are horizontally adjacent pixels).  Backward: im2col of the image gradient
+    (the patch-embedding kernel) feeds the wgrad / dgrad GEMMs; the token gradient is scattered with its bf16 twin."""
+
+    @staticmethod
+    def forward(ctx, tokens, weight, bias, Ht, Wt, p):
+        B, N, d = tokens.shape
+        Cpp = weight.shape[0]
+        C = Cpp // (p * p)
+        P = Ht * Wt
+        perm, inv = _depatch_perm(C, p, tokens.device)
+        rows = ops.gather_tokens_bf16(_as_rows_f32(tokens), 0, P)
+        w_c = bf16_of(weight).view(Cpp, d).index_select(0, perm)
+        b_c = None if bias is None else _f32c(bias).index_select(0, perm)
+        img = ops.depatchify_fwd(rows, w_c, b_c, B, Ht, Wt, p, C)
+        ctx.saved = (rows, w_c, inv)
+        ctx.dims = (B, N, d, C, P, p, tuple(weight.shape))
+        ctx.has_bias = bias is not None
+        ctx.x_needs_grad = tokens.requires_grad
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        rows, w_c, inv = ctx.saved
+        B, N, d, C, P, p, wshape = ctx.dims
+        dcols = ops.im2col_bf16(_as_rows_f32(dimg), p)             # [B*P, (c p1 p2)] bf16
+        dW_c, db_c = ops.gemm_wgrad(dcols, rows, want_bias=True)
+        dx = None
+        if ctx.x_needs_grad:
+            drows = ops.gemm_dgrad(dcols, w_c)
+            dx, dx16 = ops.scatter_tokens(drows, B, N, 0, P, want_bf16=True)
+            dx._b200_bf16_twin = (dx16, dx._version)
+        ctx.saved = None
+        return dx, dW_c.index_select(0, inv).view(wshape), (db_c.index_select(0, inv) if ctx.has_bias else None), None, None, None
 
 
 class CrossEntropyFn(torch.autograd.Function):

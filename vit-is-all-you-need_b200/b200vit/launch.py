@@ -25,7 +25,9 @@ import types
 HERE = os.path.dirname(os.path.abspath(__file__))
 SHIM = os.path.join(os.path.dirname(HERE), "shim")
 
-_SWAP = {"ViT": "ViT", "Quantizer": "Quantizer"}  # name defined by the script -> name in b200vit.modules
+# name defined by the script -> name in b200vit.modules (train_vit.py:30; train_titok.py:34,45,61 == train_vit_vqgan.py)
+_SWAP = {"ViT": "ViT", "Quantizer": "Quantizer", "TiTokEncoder": "TiTokEncoder", "TiTokDecoder": "TiTokDecoder",
+         "ViTVQGANEncoder": "TiTokEncoder", "ViTVQGANDecoder": "TiTokDecoder"}   # train_vit_vqgan.py:34,61: same code, all tokens
 
 
 def install_import_shims(reference_dir):

@@ -157,7 +157,7 @@ class ViT(nn.Module):
 
 class ViTClassifier(nn.Module):
     """train_vit.ViTClassifier (train_vit.py:47-53): head(vit(x)[:, 0]).  `head` is an ordinary nn.Linear parameter
-    container (same state_dict keys); the token gather, the tcgen05 GEMM and the backward scatter run in ClassifierHeadFn.
+    container (same state_dict keys); the token gather, the tcgen05 GEMM and the backward scatter run in TokenLinearFn.
     Like nn.Linear under autocast the logits are bf16 when autocast is on and fp32 otherwise."""
 
     def __init__(self, vit_config: ViTConfig, num_classes=1000):
@@ -166,7 +166,7 @@ class ViTClassifier(nn.Module):
         self.head = nn.Linear(vit_config.trans_config.n_embd, num_classes)
 
     def forward(self, x):
-        return Fn.ClassifierHeadFn.apply(self.vit(x), self.head.weight, self.head.bias, 0, torch.is_autocast_enabled())
+        return Fn.TokenLinearFn.apply(self.vit(x), self.head.weight, self.head.bias, 0, 1, torch.is_autocast_enabled())
 
 
 class CrossEntropyLoss(nn.Module):
@@ -222,6 +222,63 @@ class Quantizer(nn.Module):
     def forward(self, x):
         quantized, indices, _mse, _commit, total = Fn.VQFn.apply(x, self.codebook.weight, True, False, False, 0.25)
         return quantized, indices.view(x.shape[:-1]), total
+
+
+class TiTokEncoder(nn.Module):
+    """train_titok.TiTokEncoder (train_titok.py:34-43): proj(vit(x)[:, :latent_tokens]); the token slice is gathered
+    straight into the GEMM operand (TokenLinearFn).  `titok_config` is the script's own TiTokConfig."""
+
+    def __init__(self, titok_config):
+        super().__init__()
+        self.latent_tokens = titok_config.latent_tokens
+        self.vit = ViT(titok_config.enc_vit_config)
+        self.proj = nn.Linear(titok_config.n_embd, titok_config.latent_dim)
+
+    def forward(self, x):
+        y = Fn.TokenLinearFn.apply(self.vit(x), self.proj.weight, self.proj.bias, 0, self.latent_tokens,
+                                   torch.is_autocast_enabled())
+        return y.reshape(x.shape[0], self.latent_tokens, -1)
+
+
+class TiTokDecoder(nn.Module):
+    """train_titok.TiTokDecoder (train_titok.py:61-76): quant_proj, the decoder ViT over the latent "image" [B, d, L, 1]
+    with n_patches mask tokens prepended, and the de-patchify tail (1x1 conv + pixel shuffle) as one GEMM whose epilogue
+    writes the image (DepatchifyFn).  Same parameters / state_dict keys as the reference (`embd_proj` stays an nn.Conv2d)."""
+
+    def __init__(self, titok_config):
+        super().__init__()
+        self.config = titok_config
+        self.vit = ViT(titok_config.dec_vit_config)
+        self.quant_proj = nn.Linear(titok_config.latent_dim, titok_config.n_embd)
+        self.embd_proj = nn.Conv2d(titok_config.n_embd, 3 * titok_config.patch_size ** 2, kernel_size=1)
+
+    def forward(self, z):
+        z = Fn.LinearFn.apply(z, self.quant_proj.weight, self.quant_proj.bias, torch.is_autocast_enabled())
+        z = z.permute(0, 2, 1).unsqueeze(-1)                                  # 'b h c -> b c h 1'
+        tokens = self.vit(z)
+        pd = self.config.patch_dim
+        return Fn.DepatchifyFn.apply(tokens, self.embd_proj.weight, self.embd_proj.bias, pd, pd, self.config.patch_size)
+
+
+class TiTok(nn.Module):
+    """train_titok.TiTok (train_titok.py:78-92)."""
+
+    def __init__(self, titok_config):
+        super().__init__()
+        self.config = titok_config
+        self.enc = TiTokEncoder(titok_config)
+        self.quant = Quantizer(titok_config)
+        self.dec = TiTokDecoder(titok_config)
+
+    def encode(self, z): return self.quant(self.enc(z))[1]
+    def decode(self, z_quant): return self.dec(z_quant)
+    def decode_indices(self, indices): return self.dec(self.quant.codebook(indices))
+
+    def forward(self, x):
+        latent_embs = self.enc(x)
+        quantized, indices, quantize_loss = self.quant(latent_embs)
+        image_recon = self.dec(quantized)
+        return image_recon, indices, quantize_loss
 
 
 # ------------------------------------------------------------------------------------------------ blocks.py

@@ -275,24 +275,33 @@ def cast_bf16(t, out=None):
 
 
 # ---------------------------------------------------------------- classifier head + cross-entropy
-def gather_token_bf16(x, token=0):
-    """x [B, N, d] fp32 -> bf16 [B, d] rows of one token (the operand of the head GEMM, train_vit.py:53)."""
+def gather_tokens_bf16(x, t0=0, cnt=1):
+    """x [B, N, d] fp32 -> bf16 [B*cnt, d] rows of tokens t0 .. t0+cnt-1 (operand of the head / proj / de-patchify GEMMs)."""
     B, N, d = x.shape
-    out = torch.empty(B, d, device=x.device, dtype=BF16)
-    _call("b200vit_gather_token_bf16", x, ptr(_chk(x, F32, "x")), ptr(out), B, N, d, token, stream_ptr())
+    out = torch.empty(B * cnt, d, device=x.device, dtype=BF16)
+    _call("b200vit_gather_tokens_bf16", x, ptr(_chk(x, F32, "x")), ptr(out), B, N, d, t0, cnt, stream_ptr())
     return out
 
 
-def scatter_token(dy, B, N, token=0, want_bf16=True):
-    """Gradient of x[:, token]: fp32 [B, N, d] that is zero except for that token's rows, plus its bf16 twin."""
+def scatter_tokens(dy, B, N, t0=0, cnt=1, want_bf16=True):
+    """Gradient of x[:, t0:t0+cnt]: fp32 [B, N, d] that is zero outside those tokens, plus its bf16 twin."""
     d = dy.shape[-1]
-    if dy.dtype not in (BF16, F32) or not dy.is_contiguous():
-        raise TypeError("scatter_token: dy must be a contiguous bf16 or fp32 tensor")
+    if dy.dtype not in (BF16, F32) or not dy.is_contiguous() or dy.numel() != B * cnt * d:
+        raise TypeError("scatter_tokens: dy must be a contiguous bf16 or fp32 tensor of B*cnt rows")
     dx = torch.empty(B, N, d, device=dy.device, dtype=F32)
     dxb = torch.empty(B, N, d, device=dy.device, dtype=BF16) if want_bf16 else None
-    _call("b200vit_scatter_token", dy, ptr(dy), 1 if dy.dtype == BF16 else 0, ptr(dx), ptr(dxb), B, N, d, token, stream_ptr(),
+    _call("b200vit_scatter_tokens", dy, ptr(dy), 1 if dy.dtype == BF16 else 0, ptr(dx), ptr(dxb), B, N, d, t0, cnt, stream_ptr(),
           hbm_bytes=float(B * N * d * (4 + (2 if want_bf16 else 0))))
     return dx, dxb
+
+
+def depatchify_fwd(rows, w_cmajor, bias_cmajor, B, Ht, Wt, p, C):
+    """rows bf16 [B*Ht*Wt, d] x w_cmajor bf16 [C*p*p, d] (+ bias) -> image fp32 [B, C, Ht*p, Wt*p] (pixel shuffle in the epilogue)."""
+    d = rows.shape[1]
+    img = torch.empty(B, C, Ht * p, Wt * p, device=rows.device, dtype=F32)
+    _call("b200vit_depatchify_fwd", rows, ptr(_chk(rows, BF16, "rows")), ptr(_chk(w_cmajor, BF16, "w")), ptr(bias_cmajor), ptr(img),
+          B, Ht, Wt, p, C, d, stream_ptr(), flops=2.0 * rows.shape[0] * C * p * p * d)
+    return img
 
 
 def cross_entropy_fwd(logits, labels, ignore_index=-100):

@@ -52,7 +52,7 @@ static int launch(const void* A, long long lda, const void* B, long long ldb, in
 
   // output tensor maps for the TMA-store epilogue (32-row slabs of 128 bytes)
   CUtensorMap to = ta, to2 = ta;
-  if (KIND != EPI_PATCH_F32) {
+  if (!epi_direct_stores(KIND)) {
     if (epi_out_is_f32(KIND)) rc = make_tmap_2d_f32(&to, ep.out, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo, 32, 32);
     else                      rc = make_tmap_2d_bf16(&to, ep.out, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo, 32, 64);
     if (rc != OK) return rc;
@@ -109,6 +109,14 @@ int gemm_patch_epilogue(const void* xcol, const void* w, const float* bias, cons
   EpiParams ep = make_ep(out, N);
   ep.bias = bias; ep.pos = pos; ep.ldaux = N; ep.P = P; ep.T = T; ep.extra = extra;
   return launch_bn<false, false, EPI_PATCH_F32>(xcol, K, w, K, rows, N, K, ep, false, st);
+}
+
+// used by patchify.cu: y = rows @ w^T + bias written as the NCHW image (de-patchify, pixel shuffle in the epilogue)
+int gemm_depatch_epilogue(const void* rows_bf16, const void* w, const float* bias, float* img, int rows, int N, int K,
+                          int P, int Wt, int log2p, cudaStream_t st) {
+  EpiParams ep = make_ep(img, N);
+  ep.bias = bias; ep.P = P; ep.T = Wt; ep.extra = log2p;
+  return launch_bn<false, false, EPI_DEPATCH_F32>(rows_bf16, K, w, K, rows, N, K, ep, false, st);
 }
 
 }  // namespace b200

@@ -57,11 +57,15 @@ enum EpiKind : int {
   EPI_ATOMIC_F32 = 5,  // out(f32) += acc   (split-K wgrad, TMA reduce-add)
   EPI_PATCH_F32 = 6,   // out(f32)[b*T + extra + p] = acc + bias + pos[p]   (row = b*P + p), direct stores
   EPI_DROP_RESID_F32 = 7,  // out(f32) = aux(f32) + dropout(acc + bias)   (mlp[2] + nn.Dropout + residual)
+  EPI_DEPATCH_F32 = 8,     // de-patchify: out(f32)[b, c, h*p + p1, w*p + p2] = acc + bias for row = b*P + h*Wt + w and
+                           // column = c*p*p + p1*p + p2 (weight rows pre-permuted to channel-major), direct stores
 };
+
+__host__ __device__ constexpr bool epi_direct_stores(int kind) { return kind == EPI_PATCH_F32 || kind == EPI_DEPATCH_F32; }
 
 __host__ __device__ constexpr bool epi_out_is_f32(int kind) {
   return kind == EPI_RESID_F32 || kind == EPI_F32 || kind == EPI_ATOMIC_F32 || kind == EPI_PATCH_F32 ||
-         kind == EPI_DROP_RESID_F32;
+         kind == EPI_DROP_RESID_F32 || kind == EPI_DEPATCH_F32;
 }
 
 struct EpiParams {
@@ -71,7 +75,8 @@ struct EpiParams {
   const void* aux;
   long long ldaux;
   const float* pos;  // [P, N] fp32
-  int P, T, extra;
+  int P, T, extra;   // EPI_PATCH_F32: patches per image, tokens per image, extra tokens.  EPI_DEPATCH_F32: P = patches per
+                     // image, T = patches per image row (Wt), extra = log2(patch size)
   uint32_t drop_seed, drop_thr;  // EPI_DROP_RESID_F32: counter-based mask (dropout.cuh)
   float drop_r;                  // 1 / (1 - p)
   float* colsum;     // wgrad only: colsum[m] += sum_k A(m, k)  (= bias gradient, summed from the smem A tiles)
@@ -226,7 +231,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if (KIND != EPI_PATCH_F32) tma_prefetch_desc(&tma_out);
+    if (!epi_direct_stores(KIND)) tma_prefetch_desc(&tma_out);
     if (KIND == EPI_GELU_BF16) tma_prefetch_desc(&tma_out2);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], (NCTA == 2 && leader) ? 2 : 1);  // own producer (+ the peer's relay)
@@ -445,7 +450,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vbuf[c & 1][j]);
           if constexpr (KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_RESID_F32 || KIND == EPI_F32 ||
-                        KIND == EPI_PATCH_F32 || KIND == EPI_DROP_RESID_F32) {
+                        KIND == EPI_PATCH_F32 || KIND == EPI_DROP_RESID_F32 || KIND == EPI_DEPATCH_F32) {
             if (ep.bias != nullptr) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
@@ -468,6 +473,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                   const float4 a = __ldg(reinterpret_cast<const float4*>(pe) + q);
                   reinterpret_cast<float4*>(o)[q] = make_float4(v[q * 4 + 0] + a.x, v[q * 4 + 1] + a.y,
                                                                 v[q * 4 + 2] + a.z, v[q * 4 + 3] + a.w);
+                }
+              }
+            }
+          } else if constexpr (KIND == EPI_DEPATCH_F32) {
+            // pixel shuffle in the store addresses: 4 consecutive columns = 4 horizontally adjacent pixels of one
+            // channel; the 32 lanes of the warp hold horizontally adjacent patches, so the 4-float runs of a store
+            // instruction tile whole 128-byte lines of an image row between them (p >= 4, power of two)
+            if (row_ok) {
+              const int lp = ep.extra, p = 1 << lp, Wt = ep.T;
+              const int b = row / ep.P, pp = row - b * ep.P;
+              const int ph = pp / Wt, pw = pp - ph * Wt;
+              const int Himg = (ep.P / Wt) << lp, Wimg = Wt << lp, C = s.N >> (2 * lp);
+              float* img = reinterpret_cast<float*>(ep.out) + (long long)b * C * Himg * Wimg;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int n = col + q * 4;
+                if (n < s.N) {
+                  const int c = n >> (2 * lp), rem = n & ((1 << (2 * lp)) - 1);
+                  const int p1 = rem >> lp, p2 = rem & (p - 1);
+                  float* o = img + ((long long)c * Himg + (ph << lp) + p1) * Wimg + (pw << lp) + p2;
+                  *reinterpret_cast<float4*>(o) = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
                 }
               }
             }

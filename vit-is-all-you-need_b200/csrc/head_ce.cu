@@ -1,14 +1,15 @@
 // Classifier head plumbing + cross-entropy: the steps immediately after the encoder stack.
 //
-//   train_vit.py:51-53   ViTClassifier.forward: head(vit(x)[:, 0])       -> gather_token (fp32 rows -> bf16 GEMM operand),
-//                                                                           tcgen05 GEMM (gemm.cu), scatter_token (backward)
+//   train_vit.py:51-53   ViTClassifier.forward: head(vit(x)[:, 0])       -> gather_tokens (fp32 rows -> bf16 GEMM operand),
+//                                                                           tcgen05 GEMM (gemm.cu), scatter_tokens (backward)
 //   train_vit.py:81,102  nn.CrossEntropyLoss()(pred, labels)             -> cross_entropy_fwd / _bwd
 //   train_videogpt.py:53-54 cross entropy over [B*1024, 1024] logits     -> same kernels (one warp per row)
 //
 // All HBM-bound and small next to the stack; the point of fusing them is launch count and the backward fill: the
 // gradient of `x[:, 0]` is a [B, N, d] tensor that is zero except for one row per image, which PyTorch produces with a
 // fill + a strided copy and the stack's backward then casts to bf16 (three passes over 155 MB at ViT-B/16, B = 256);
-// scatter_token writes the fp32 tensor and its bf16 twin in one pass.
+// scatter_tokens writes the fp32 tensor and its bf16 twin in one pass.  Both take a token RANGE: the tokenizer encoder
+// projects the first `latent_tokens` tokens (train_titok.py:41-42), the decoder de-patchifies the first `n_patches` (train_titok.py:71).
 //
 // Cross-entropy follows torch.nn.functional.cross_entropy (reduction='mean', ignore_index, no label smoothing, no class
 // weights -- what every reference script uses): row loss = logsumexp(x) - x[label], mean over the non-ignored rows;
@@ -18,26 +19,27 @@
 
 namespace b200 {
 
+// out[b * cnt + t, :] = bf16(x[b, t0 + t, :]) for t in [0, cnt): the cnt * d values of one image are contiguous in x
 __global__ void __launch_bounds__(256)
-gather_token_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, long long img_stride, int d,
-                    long long token_off) {
-  const int per_row = d >> 2;
-  const long long total = (long long)B * per_row;
+gather_tokens_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, long long img_stride,
+                     long long per_img /* cnt * d */, long long token_off) {
+  const long long per4 = per_img >> 2;
+  const long long total = (long long)B * per4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / per_row;
-    const int c = (int)(i - b * per_row) * 4;
+    const long long b = i / per4;
+    const long long c = (i - b * per4) * 4;
     const float4 v = *reinterpret_cast<const float4*>(x + b * img_stride + token_off + c);
     uint2 w;
     w.x = pack_bf16(v.x, v.y); w.y = pack_bf16(v.z, v.w);
-    *reinterpret_cast<uint2*>(out + b * d + c) = w;
+    *reinterpret_cast<uint2*>(out + b * per_img + c) = w;
   }
 }
 
-// dx[B, N, d] (fp32) = 0 except dx[:, token] = dy ; optional bf16 twin.  One pass of pure stores.
+// dx[B, N, d] (fp32) = 0 except dx[:, t0 : t0 + cnt] = dy[B * cnt, d] ; optional bf16 twin.  One pass of pure stores.
 template <bool DY_BF16>
 __global__ void __launch_bounds__(256)
-scatter_token_kernel(const void* __restrict__ dy_, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int B, int N,
-                     int d, int token) {
+scatter_tokens_kernel(const void* __restrict__ dy_, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx16, int B, int N,
+                      int d, int t0, int cnt) {
   const int per_row = d >> 2;
   const long long total = (long long)B * N * per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -46,13 +48,14 @@ scatter_token_kernel(const void* __restrict__ dy_, float* __restrict__ dx, __nv_
     const long long b = row / N;
     const int t = (int)(row - b * N);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t == token) {
+    if (t >= t0 && t < t0 + cnt) {
+      const long long src = (b * cnt + (t - t0)) * d + c;
       if constexpr (DY_BF16) {
-        const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy_) + b * d + c);
+        const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(dy_) + src);
         const float2 p0 = unpack_bf16(u.x), p1 = unpack_bf16(u.y);
         v = make_float4(p0.x, p0.y, p1.x, p1.y);
       } else {
-        v = *reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + b * d + c);
+        v = *reinterpret_cast<const float4*>(static_cast<const float*>(dy_) + src);
       }
     }
     *reinterpret_cast<float4*>(dx + row * d + c) = v;
@@ -144,27 +147,29 @@ using namespace b200;
 
 extern "C" {
 
-int b200vit_gather_token_bf16(const float* x, void* out_bf16, int B, int N, int d, int token, void* stream) {
-  B200_REQUIRE(x && out_bf16 && B > 0 && N > 0 && d > 0 && d % 4 == 0 && token >= 0 && token < N,
-               "gather_token: bad arguments (d must be a multiple of 4, 0 <= token < N)");
-  const long long total = (long long)B * (d / 4);
-  const int grid = (int)((total + 255) / 256);
-  gather_token_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_bf16, B, (long long)N * d, d,
-                                                              (long long)token * d);
+int b200vit_gather_tokens_bf16(const float* x, void* out_bf16, int B, int N, int d, int t0, int cnt, void* stream) {
+  B200_REQUIRE(x && out_bf16 && B > 0 && N > 0 && d > 0 && d % 4 == 0 && t0 >= 0 && cnt > 0 && t0 + cnt <= N,
+               "gather_tokens: bad arguments (d must be a multiple of 4, 0 <= t0, t0 + cnt <= N)");
+  const long long total = (long long)B * cnt * (d / 4);
+  const long long want = (total + 255) / 256;
+  const int cap = num_sms() * 16;
+  const int grid = (int)(want < cap ? want : cap);
+  gather_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_bf16, B, (long long)N * d,
+                                                               (long long)cnt * d, (long long)t0 * d);
   B200_CUDA(cudaGetLastError());
   return OK;
 }
 
-int b200vit_scatter_token(const void* dy, int dy_is_bf16, float* dx, void* dx_bf16, int B, int N, int d, int token,
-                          void* stream) {
-  B200_REQUIRE(dy && dx && B > 0 && N > 0 && d > 0 && d % 4 == 0 && token >= 0 && token < N,
-               "scatter_token: bad arguments (d must be a multiple of 4, 0 <= token < N)");
+int b200vit_scatter_tokens(const void* dy, int dy_is_bf16, float* dx, void* dx_bf16, int B, int N, int d, int t0, int cnt,
+                           void* stream) {
+  B200_REQUIRE(dy && dx && B > 0 && N > 0 && d > 0 && d % 4 == 0 && t0 >= 0 && cnt > 0 && t0 + cnt <= N,
+               "scatter_tokens: bad arguments (d must be a multiple of 4, 0 <= t0, t0 + cnt <= N)");
   const long long total = (long long)B * N * (d / 4);
   const long long want = (total + 255) / 256;
   const int cap = num_sms() * 16;
   const int grid = (int)(want < cap ? want : cap);
-  if (dy_is_bf16) scatter_token_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dx, (__nv_bfloat16*)dx_bf16, B, N, d, token);
-  else            scatter_token_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dx, (__nv_bfloat16*)dx_bf16, B, N, d, token);
+  if (dy_is_bf16) scatter_tokens_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dx, (__nv_bfloat16*)dx_bf16, B, N, d, t0, cnt);
+  else            scatter_tokens_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dx, (__nv_bfloat16*)dx_bf16, B, N, d, t0, cnt);
   B200_CUDA(cudaGetLastError());
   return OK;
 }

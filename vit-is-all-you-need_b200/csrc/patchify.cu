@@ -10,6 +10,9 @@ namespace b200 {
 int gemm_patch_epilogue(const void* xcol, const void* w, const float* bias, const float* pos, float* out,
                         int rows, int N, int K, int P, int T, int extra, cudaStream_t st);
 
+int gemm_depatch_epilogue(const void* rows_bf16, const void* w, const float* bias, float* img, int rows, int N, int K,
+                          int P, int Wt, int log2p, cudaStream_t st);
+
 // cols[(b, ph, pw), (c, i, j)] = x[b, c, ph*p + i, pw*p + j]   (fp32 -> bf16), 4 pixels per thread
 __global__ void im2col_vec4_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ cols, int B, int C,
                                    int H, int W, int p) {
@@ -168,6 +171,17 @@ int b200vit_patch_embed_fwd(const float* x, const void* w_bf16, const float* bia
     B200_CUDA(cudaGetLastError());
   }
   return gemm_patch_epilogue(cols, w_bf16, bias, pos_emb, tokens, B * P, d, K, P, T, extra, st);
+}
+
+int b200vit_depatchify_fwd(const void* rows_bf16, const void* w_cmajor_bf16, const float* bias_cmajor, float* img, int B,
+                           int Ht, int Wt, int p, int C, int d, void* stream) {
+  B200_REQUIRE(rows_bf16 && w_cmajor_bf16 && img && B > 0 && Ht > 0 && Wt > 0 && C > 0, "depatchify_fwd: bad arguments");
+  int log2p = 0;
+  while ((1 << log2p) < p) ++log2p;
+  B200_REQUIRE(p >= 4 && (1 << log2p) == p, "depatchify_fwd: patch size %d must be a power of two >= 4", p);
+  B200_REQUIRE(d % 8 == 0, "depatchify_fwd: d=%d must be a multiple of 8", d);
+  return gemm_depatch_epilogue(rows_bf16, w_cmajor_bf16, bias_cmajor, img, B * Ht * Wt, C * p * p, d, Ht * Wt, Wt, log2p,
+                               (cudaStream_t)stream);
 }
 
 int b200vit_patch_embed_bwd_reduce(const float* dtokens, float* dsum, void* dpe_bf16, int B, int T, int extra, int d,
