@@ -161,6 +161,14 @@ int b200vit_cross_entropy_bwd(const void* logits, int logits_bf16, long long ld,
                               const float* loss, const float* dloss, void* dlogits, long long ldd, int R, int C,
                               long long ignore_index, void* stream);
 
+/* token + positional embedding of the autoregressive models (train_videogpt.py:45-50):
+ * out[b, s, :] = tok_embed[idx[b, s]] + pos_embed[pos0 + s] (fp32);  backward: dtok[vocab, d] (overwritten, fp32 atomics
+ * over repeated tokens) and dpos[S, d] = sum_b dy[b, s].                                                       */
+int b200vit_embed_fwd(const long long* idx, const float* tok_embed, const float* pos_embed, float* out, int B, int S, int d,
+                      int pos0, int vocab, void* stream);
+int b200vit_embed_bwd(const long long* idx, const float* dy, float* dtok, float* dpos, int B, int S, int d, int vocab,
+                      void* stream);
+
 /* ---- fused multi-tensor AdamW + bf16 operand refresh (torch.optim.AdamW at train_vit.py:82,105, ------------
  * train_titok.py:134,160, train_videogpt.py:107,134; arithmetic of torch/optim/adam.py::_single_tensor_adam)
  * tensors: device array of { float* p; const float* g; float* m; float* v; bf16* w16 (or NULL); long long n } ;

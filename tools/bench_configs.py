@@ -76,9 +76,46 @@ def stack_step(name, cfg, B, N, causal):
     torch.cuda.empty_cache()
 
 
+class _TiTokCfg:   # train_titok.TiTokConfig (train_titok.py:18-32)
+    def __init__(self, image_size, patch_size, latent_tokens, codebook_size, latent_dim, transformer):
+        self.image_size, self.patch_size, self.latent_tokens = image_size, patch_size, latent_tokens
+        self.codebook_size, self.latent_dim, self.transformer = codebook_size, latent_dim, transformer
+        self.patch_dim = image_size // patch_size
+        self.n_patches = self.patch_dim ** 2
+        self.enc_vit_config = M.ViTConfig(image_size, 3, patch_size, transformer, latent_tokens, 0.0)
+        self.n_embd = self.enc_vit_config.trans_config.n_embd
+        self.dec_vit_config = M.ViTConfig(latent_tokens, self.n_embd, 1, transformer, self.n_patches, 0.0)
+        self.dec_vit_config.n_patches = latent_tokens
+
+
+def titok_step(name, B):
+    """configs[2]: train_titok.py:152-160 without the LPIPS/ConvNeXt perceptual term (out of scope): recon = MSE + L1 + VQ loss."""
+    from b200vit.optim import AdamW
+    torch.manual_seed(0)
+    cfg = _TiTokCfg(256, 16, 32, 4096, 12, "S")
+    net = M.TiTok(cfg).to(dev)
+    opt = AdamW(net.parameters(), lr=1e-4)
+    x = torch.rand(B, 3, 256, 256, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            recon, idx, qloss = net(x)
+            loss = torch.nn.functional.mse_loss(recon, x) + torch.nn.functional.l1_loss(recon, x) + qloss
+        loss.backward()
+        opt.step()
+    ms = timeit(step)
+    N = 288
+    fl = 3 * 12 * layer_flops(N, 512) * B
+    rows.append((name, f"{ms:.2f} ms/step", f"{B / ms * 1e3:.0f} img/s", f"{fl / ms / 1e9:.0f} TFLOP/s (transformer layers only)"))
+    del net, opt
+    torch.cuda.empty_cache()
+
+
 vit_step("configs[0] ViT-Ti/4 32px, batch 32 (fwd+CE+bwd+AdamW)", 32, 4, "Ti", 32, 10)
 vit_step("configs[0] shape at batch 4096", 32, 4, "Ti", 4096, 10)
 vit_step("configs[3] ViT-L/16 224px, batch 256 (fwd+CE+bwd+AdamW)", 224, 16, "L", 256, 1000)
+titok_step("configs[2] TiTok-S 256px tokenizer, 32 latent tokens, K=4096: enc + VQ + dec, fwd+bwd+AdamW, batch 256", 256)
 stack_step("configs[2] TiTok-S encoder stack, N=288 (32 latent + 256 patches), batch 256", M.S(block_size=288), 256, 288, False)
 stack_step("configs[4] VideoGPT-B causal stack, N=1024, batch 16", M.B(block_size=1024, causal=True), 16, 1024, True)
 

@@ -19,7 +19,7 @@ launch_count = 0  # number of C-ABI compute calls issued (bench.py reports it as
 
 
 # kernels launched per C-ABI call (memsets not counted); everything else launches exactly one kernel
-_KERNELS_PER_CALL = {"b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3, "b200vit_cross_entropy_fwd": 2}
+_KERNELS_PER_CALL = {"b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3, "b200vit_cross_entropy_fwd": 2, "b200vit_embed_bwd": 2}
 
 _prof = None  # list of (start_event, end_event, flops) while profile_gemms() is active
 
@@ -302,6 +302,28 @@ def depatchify_fwd(rows, w_cmajor, bias_cmajor, B, Ht, Wt, p, C):
     _call("b200vit_depatchify_fwd", rows, ptr(_chk(rows, BF16, "rows")), ptr(_chk(w_cmajor, BF16, "w")), ptr(bias_cmajor), ptr(img),
           B, Ht, Wt, p, C, d, stream_ptr(), flops=2.0 * rows.shape[0] * C * p * p * d)
     return img
+
+
+def embed_fwd(idx, tok_embed, pos_embed, pos0=0):
+    """idx [B, S] int64 -> fp32 [B, S, d] = tok_embed[idx] + pos_embed[pos0 : pos0 + S] (train_videogpt.py:50)."""
+    B, S = idx.shape
+    V, d = tok_embed.shape
+    if pos0 + S > pos_embed.shape[0]:
+        raise ValueError(f"embed_fwd: positions {pos0}..{pos0 + S - 1} exceed pos_embed ({pos_embed.shape[0]} rows)")
+    out = torch.empty(B, S, d, device=tok_embed.device, dtype=F32)
+    _call("b200vit_embed_fwd", tok_embed, ptr(_chk(idx, torch.int64, "idx")), ptr(_chk(tok_embed, F32, "tok_embed")),
+          ptr(_chk(pos_embed, F32, "pos_embed")), ptr(out), B, S, d, pos0, V, stream_ptr())
+    return out
+
+
+def embed_bwd(idx, dy, vocab, n_pos):
+    """(d tok_embed [vocab, d], d pos_embed [n_pos, d]) for embed_fwd with pos0 = 0."""
+    B, S, d = dy.shape
+    dtok = torch.empty(vocab, d, device=dy.device, dtype=F32)
+    dpos = torch.zeros(n_pos, d, device=dy.device, dtype=F32) if n_pos != S else torch.empty(S, d, device=dy.device, dtype=F32)
+    _call("b200vit_embed_bwd", dy, ptr(_chk(idx, torch.int64, "idx")), ptr(_chk(dy, F32, "dy")), ptr(dtok), ptr(dpos), B, S, d, vocab,
+          stream_ptr())
+    return dtok, dpos
 
 
 def cross_entropy_fwd(logits, labels, ignore_index=-100):

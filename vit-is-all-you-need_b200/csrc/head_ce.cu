@@ -201,3 +201,91 @@ int b200vit_cross_entropy_bwd(const void* logits, int logits_bf16, long long ld,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------
+// Token + positional embedding of the autoregressive models (train_videogpt.py:45-50):
+//   x[b, s, :] = tok_embed[idx[b, s]] + pos_embed[pos0 + s]          (fp32 residual stream, the stack's input)
+// backward: d_tok_embed[idx[b, s]] += dy[b, s]  (fp32 atomics; rows repeat across the batch),
+//           d_pos_embed[pos0 + s]   = sum_b dy[b, s]
+// ------------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+__global__ void __launch_bounds__(256)
+embed_fwd_kernel(const long long* __restrict__ idx, const float* __restrict__ tok, const float* __restrict__ pos,
+                 float* __restrict__ out, long long rows, int S, int d, int pos0, int vocab) {
+  const int per_row = d >> 2;
+  const long long total = rows * per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / per_row;
+    const int c = (int)(i - r * per_row) * 4;
+    long long t = idx[r];
+    t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);   // host validates; never read out of bounds
+    const int s = (int)(r % S);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(tok + t * d + c));
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (long long)(pos0 + s) * d + c));
+    *reinterpret_cast<float4*>(out + r * d + c) = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+embed_bwd_tok_kernel(const long long* __restrict__ idx, const float* __restrict__ dy, float* __restrict__ dtok, long long rows,
+                     int d, int vocab) {
+  const long long total = rows * d;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / d;
+    const int c = (int)(i - r * d);
+    const long long t = idx[r];
+    if (t >= 0 && t < vocab) atomicAdd(dtok + t * d + c, dy[i]);
+  }
+}
+
+// dpos[s, :] = sum_b dy[b, s, :]   (deterministic: one thread per output element walks the batch)
+__global__ void __launch_bounds__(256)
+embed_bwd_pos_kernel(const float* __restrict__ dy, float* __restrict__ dpos, int B, int S, int d) {
+  const int per_row = d >> 2;
+  const long long total = (long long)S * per_row;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long off = i * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; ++b) {
+    const float4 v = *reinterpret_cast<const float4*>(dy + (long long)b * S * d + off);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dpos + off) = acc;
+}
+
+}  // namespace b200
+
+extern "C" {
+
+int b200vit_embed_fwd(const long long* idx, const float* tok_embed, const float* pos_embed, float* out, int B, int S, int d,
+                      int pos0, int vocab, void* stream) {
+  B200_REQUIRE(idx && tok_embed && pos_embed && out && B > 0 && S > 0 && d > 0 && d % 4 == 0 && pos0 >= 0 && vocab > 0,
+               "embed_fwd: bad arguments (d must be a multiple of 4)");
+  const long long total = (long long)B * S * (d / 4);
+  const long long want = (total + 255) / 256;
+  const int cap = b200::num_sms() * 16;
+  b200::embed_fwd_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(idx, tok_embed, pos_embed, out,
+                                                                                         (long long)B * S, S, d, pos0, vocab);
+  B200_CUDA(cudaGetLastError());
+  return b200::OK;
+}
+
+int b200vit_embed_bwd(const long long* idx, const float* dy, float* dtok /* [vocab, d], overwritten */, float* dpos /* [S, d] */,
+                      int B, int S, int d, int vocab, void* stream) {
+  B200_REQUIRE(idx && dy && dtok && dpos && B > 0 && S > 0 && d > 0 && d % 4 == 0 && vocab > 0, "embed_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA(cudaMemsetAsync(dtok, 0, sizeof(float) * (size_t)vocab * d, st));
+  const long long total = (long long)B * S * d;
+  const long long want = (total + 255) / 256;
+  const int cap = b200::num_sms() * 16;
+  b200::embed_bwd_tok_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(idx, dy, dtok, (long long)B * S, d, vocab);
+  B200_CUDA(cudaGetLastError());
+  const long long tp = (long long)S * (d / 4);
+  b200::embed_bwd_pos_kernel<<<(int)((tp + 255) / 256), 256, 0, st>>>(dy, dpos, B, S, d);
+  B200_CUDA(cudaGetLastError());
+  return b200::OK;
+}
+
+}  // extern "C"
