@@ -169,6 +169,11 @@ int b200vit_embed_fwd(const long long* idx, const float* tok_embed, const float*
 int b200vit_embed_bwd(const long long* idx, const float* dy, float* dtok, float* dpos, int B, int S, int d, int vocab,
                       void* stream);
 
+/* incremental decode attention for VideoGPT.generate (train_videogpt.py:56-65): kv_cache[B, Nmax, 3, H, 64] bf16 in the
+ * layout of the fused QKV projection (row `pos` already holds q, k, v of the new token);
+ * out_bf16[B, H*64] = softmax(q_pos . K[0..pos]^T / 8) V[0..pos].                                              */
+int b200vit_attn_decode(const void* kv_cache, void* out_bf16, int B, int Nmax, int H, int pos, void* stream);
+
 /* ---- fused multi-tensor AdamW + bf16 operand refresh (torch.optim.AdamW at train_vit.py:82,105, ------------
  * train_titok.py:134,160, train_videogpt.py:107,134; arithmetic of torch/optim/adam.py::_single_tensor_adam)
  * tensors: device array of { float* p; const float* g; float* m; float* v; bf16* w16 (or NULL); long long n } ;

@@ -475,3 +475,16 @@ def test_depatchify_gemm_epilogue(ops, B, Ht, Wt, p, C, d):
     img = ops.depatchify_fwd(to_dev(rows, torch.bfloat16), to_dev(w_ref[perm], torch.bfloat16), to_dev(b_ref[perm]), B, Ht, Wt, p, C)
     assert img.shape == (B, C, Ht * p, Wt * p)
     assert_close_bf16(img, img_ref, "de-patchified image", rel=2e-5)
+
+
+@pytest.mark.parametrize("B,H,Nmax,pos", [(3, 2, 40, 0), (2, 12, 64, 17), (4, 1, 300, 299), (1, 3, 1024, 1023)])
+def test_attn_decode_against_oracle(ops, B, H, Nmax, pos):
+    # one query (the row at `pos`) against the cached keys / values 0..pos: oracle sdpa_fwd on the same bf16 values
+    rng = np.random.default_rng(B + H + pos)
+    cache = bf16_round(rng.standard_normal((B, Nmax, 3, H, 64)).astype(np.float32))
+    o = ops.attn_decode(to_dev(cache, torch.bfloat16), pos)
+    q = cache[:, pos:pos + 1, 0].transpose(0, 2, 1, 3).astype(np.float64)           # [B, H, 1, 64]
+    k = cache[:, :pos + 1, 1].transpose(0, 2, 1, 3).astype(np.float64)
+    v = cache[:, :pos + 1, 2].transpose(0, 2, 1, 3).astype(np.float64)
+    ref, _ = O.sdpa_fwd(q, k, v, causal=False)                                      # [B, H, 1, 64]
+    assert_close_bf16(o, ref[:, :, 0].reshape(B, H * 64), "decode attention", rel=5e-3)

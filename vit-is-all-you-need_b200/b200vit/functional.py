@@ -454,6 +454,60 @@ class DepatchifyFn(torch.autograd.Function):
         return dx, dW_c.index_select(0, inv).view(wshape), (db_c.index_select(0, inv) if ctx.has_bias else None), None, None, None
 
 
+# ------------------------------------------------------------------------------------------------------------
+# Inference-only helpers for VideoGPT.generate (train_videogpt.py:56-65): prefill that keeps every layer's fused QKV rows
+# as the KV cache, and the single-token step over that cache.  dropout must be 0 (the reference's generate() is otherwise
+# stochastic even in eval mode, transformer.py:28).
+# ------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def stack_prefill(x, layers, n_heads, n_max):
+    """x [B, S, d] fp32 through the causal stack; returns (h [B, S, d] fp32, caches: one [B, n_max, 3, H, 64] bf16 per layer)."""
+    B, S, d = x.shape
+    h = _as_rows_f32(x).view(B * S, d)
+    caches = []
+    for P in layers:
+        h, saved = layer_forward(h, P, B, S, n_heads, True, True)
+        qkv = saved[2]                                             # [B*S, 3d] bf16 == [B, S, 3, H, 64]
+        cache = torch.empty(B, n_max, 3, n_heads, 64, device=x.device, dtype=BF16)
+        cache[:, :S].copy_(qkv.view(B, S, 3, n_heads, 64))
+        caches.append(cache)
+    return h.view(B, S, d), caches
+
+
+@torch.no_grad()
+def stack_decode_step(x, layers, caches, pos):
+    """One new token per sequence: x [B, d] fp32 at position `pos`; appends its k, v to the caches, returns [B, d] fp32."""
+    B, d = x.shape
+    h = _as_rows_f32(x)
+    for P, cache in zip(layers, caches):
+        a, _, _, _, _ = ops.layernorm_fwd(h)
+        qkv = ops.gemm_bias(a, bf16_of(P.qkv_w), _f32c(P.qkv_b))   # [B, 3d]
+        cache[:, pos].copy_(qkv.view(B, 3, cache.shape[3], 64))
+        o = ops.attn_decode(cache, pos)
+        b, _, _, _, x1 = ops.layernorm_fwd(h, add=o, want_x_out=True)
+        g, _ = ops.gemm_bias_gelu(b, bf16_of(P.fc1_w), _f32c(P.fc1_b))
+        h = ops.gemm_bias_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1)
+    return h
+
+
+class EmbedFn(torch.autograd.Function):
+    """tok_embed(idx) + pos_embed(arange(S)) (train_videogpt.py:50) -> fp32 [B, S, d], the stack's input."""
+
+    @staticmethod
+    def forward(ctx, idx, tok_embed, pos_embed):
+        idx = idx.contiguous()
+        ctx.saved = (idx,)
+        ctx.dims = (tok_embed.shape[0], pos_embed.shape[0])
+        return ops.embed_fwd(idx, _f32c(tok_embed), _f32c(pos_embed), 0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved
+        vocab, n_pos = ctx.dims
+        dtok, dpos = ops.embed_bwd(idx, _as_rows_f32(dy), vocab, n_pos)
+        return None, dtok, dpos
+
+
 class CrossEntropyFn(torch.autograd.Function):
     """F.cross_entropy(logits, labels) with reduction='mean' and ignore_index (train_vit.py:81,102, train_videogpt.py:54)."""
 

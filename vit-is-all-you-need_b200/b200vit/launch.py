@@ -27,7 +27,7 @@ SHIM = os.path.join(os.path.dirname(HERE), "shim")
 
 # name defined by the script -> name in b200vit.modules (train_vit.py:30; train_titok.py:34,45,61 == train_vit_vqgan.py)
 _SWAP = {"ViT": "ViT", "Quantizer": "Quantizer", "TiTokEncoder": "TiTokEncoder", "TiTokDecoder": "TiTokDecoder",
-         "ViTVQGANEncoder": "TiTokEncoder", "ViTVQGANDecoder": "TiTokDecoder"}   # train_vit_vqgan.py:34,61: same code, all tokens
+         "ViTVQGANEncoder": "TiTokEncoder", "ViTVQGANDecoder": "TiTokDecoder", "VideoGPT": "VideoGPT"}   # train_vit_vqgan.py:34,61: same code, all tokens
 
 
 def install_import_shims(reference_dir):

@@ -281,6 +281,75 @@ class TiTok(nn.Module):
         return image_recon, indices, quantize_loss
 
 
+# ------------------------------------------------------------------------------------------------ train_videogpt.py
+class VideoGPT(nn.Module):
+    """train_videogpt.VideoGPT (train_videogpt.py:38-69): token + positional embedding, causal Transformer, vocabulary
+    projection, cross-entropy -- and generate() with a KV cache instead of the reference's full re-computation per token
+    (same greedy tokens).  `config` is the script's own VideoGPTConfig (codebook_size, n_embd, max_tokens, trans_config,
+    frame_size)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.tok_embed = nn.Embedding(config.codebook_size + 1, config.n_embd)
+        self.pos_embed = nn.Embedding(config.max_tokens, config.n_embd)
+        self.transformer = Transformer(config.trans_config)
+        self.proj = nn.Linear(config.n_embd, config.codebook_size)
+
+    def _layers(self):
+        return [Fn.LayerParams(*layer._params()) for layer in self.transformer.layers]
+
+    def forward(self, x):
+        B, T, N = x.shape
+        S = T * N
+        y = x.reshape(B, S)
+        sos = torch.full((B, 1), self.config.codebook_size, device=x.device, dtype=torch.long)
+        inp = torch.cat([sos, y[:, :-1]], dim=-1)
+        h = Fn.EmbedFn.apply(inp, self.tok_embed.weight, self.pos_embed.weight[:S])
+        h = self.transformer(h)
+        logits = Fn.TokenLinearFn.apply(h, self.proj.weight, self.proj.bias, 0, S, torch.is_autocast_enabled())
+        loss = Fn.CrossEntropyFn.apply(logits, y.reshape(-1), -100)
+        return logits.reshape(B, S, -1), loss
+
+    @torch.no_grad()
+    def generate(self, tokens, n=1):
+        """Greedy continuation of tokens [B, T0] by n tokens (train_videogpt.py:56-65), KV-cached: one prefill over
+        [sos, tokens], then one single-token step per generated token."""
+        if n <= 0:
+            return tokens
+        if float(self.transformer.dropout) > 0.0:
+            raise NotImplementedError("generate() with dropout > 0 is stochastic in the reference (SDPA dropout_p is applied "
+                                      "in eval mode, transformer.py:28); the KV-cached path implements dropout = 0")
+        B, T0 = tokens.shape
+        total = T0 + n            # the last step of the reference embeds T0 + n positions
+        if total > self.pos_embed.weight.shape[0]:
+            raise ValueError(f"generate: {total} positions exceed max_tokens={self.pos_embed.weight.shape[0]}")
+        layers, H = self._layers(), self.transformer.n_heads
+        wproj, bproj = Fn.bf16_of(self.proj.weight), Fn._f32c(self.proj.bias)
+
+        def next_token(h_last):   # h_last [B, d] fp32 -> greedy token [B, 1]
+            logits = Fn.ops.gemm_bias_f32(Fn.ops.cast_bf16(h_last.contiguous()), wproj, bproj)
+            return torch.argmax(logits, dim=-1, keepdim=True)
+
+        sos = torch.full((B, 1), self.config.codebook_size, device=tokens.device, dtype=torch.long)
+        inp = torch.cat([sos, tokens], dim=-1)                                     # [B, T0 + 1]
+        h = Fn.ops.embed_fwd(inp.contiguous(), Fn._f32c(self.tok_embed.weight), Fn._f32c(self.pos_embed.weight), 0)
+        h, caches = Fn.stack_prefill(h, layers, H, total)
+        new = next_token(h[:, -1])
+        out = [tokens, new]
+        for j in range(1, n):
+            pos = T0 + j                                                           # position of the token generated last
+            x = Fn.ops.embed_fwd(new.contiguous(), Fn._f32c(self.tok_embed.weight), Fn._f32c(self.pos_embed.weight), pos)
+            h1 = Fn.stack_decode_step(x.view(B, -1), layers, caches, pos)
+            new = next_token(h1)
+            out.append(new)
+        return torch.cat(out, dim=-1)
+
+    def generate_frames(self, video_tokens, n=1):
+        tokens = video_tokens.reshape(video_tokens.shape[0], -1)
+        return self.generate(tokens, n * self.config.frame_size)
+
+
 # ------------------------------------------------------------------------------------------------ blocks.py
 class ResidualAttentionBlock(nn.Module):
     """blocks.ResidualAttentionBlock (blocks.py:32-70); x is sequence-first [L, B, d]."""

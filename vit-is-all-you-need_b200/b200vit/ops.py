@@ -274,6 +274,18 @@ def cast_bf16(t, out=None):
     return out
 
 
+# ---------------------------------------------------------------- KV-cached decode
+def attn_decode(kv_cache, pos):
+    """kv_cache [B, Nmax, 3, H, 64] bf16 (row `pos` holds the new token's q, k, v) -> o [B, H*64] bf16."""
+    B, Nmax, three, H, hd = kv_cache.shape
+    if three != 3 or hd != 64:
+        raise ValueError("attn_decode: cache must be [B, Nmax, 3, H, 64]")
+    out = torch.empty(B, H * 64, device=kv_cache.device, dtype=BF16)
+    _call("b200vit_attn_decode", kv_cache, ptr(_chk(kv_cache, BF16, "kv_cache")), ptr(out), B, Nmax, H, pos, stream_ptr(),
+          hbm_bytes=float(B * H * (pos + 1) * 256))
+    return out
+
+
 # ---------------------------------------------------------------- classifier head + cross-entropy
 def gather_tokens_bf16(x, t0=0, cnt=1):
     """x [B, N, d] fp32 -> bf16 [B*cnt, d] rows of tokens t0 .. t0+cnt-1 (operand of the head / proj / de-patchify GEMMs)."""
