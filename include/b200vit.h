@@ -165,14 +165,18 @@ int b200vit_cross_entropy_bwd(const void* logits, int logits_bf16, long long ld,
  * out[b, s, :] = tok_embed[idx[b, s]] + pos_embed[pos0 + s] (fp32);  backward: dtok[vocab, d] (overwritten, fp32 atomics
  * over repeated tokens) and dpos[S, d] = sum_b dy[b, s].                                                       */
 int b200vit_embed_fwd(const long long* idx, const float* tok_embed, const float* pos_embed, float* out, int B, int S, int d,
-                      int pos0, int vocab, void* stream);
+                      int pos0, const int* pos0_dev /* optional: position from device memory (graph-captured decode) */,
+                      int n_pos, int vocab, void* stream);
 int b200vit_embed_bwd(const long long* idx, const float* dy, float* dtok, float* dpos, int B, int S, int d, int vocab,
                       void* stream);
 
 /* incremental decode attention for VideoGPT.generate (train_videogpt.py:56-65): kv_cache[B, Nmax, 3, H, 64] bf16 in the
- * layout of the fused QKV projection (row `pos` already holds q, k, v of the new token);
- * out_bf16[B, H*64] = softmax(q_pos . K[0..pos]^T / 8) V[0..pos].                                              */
-int b200vit_attn_decode(const void* kv_cache, void* out_bf16, int B, int Nmax, int H, int pos, void* stream);
+ * layout of the fused QKV projection; kv_append writes the new token's fused q|k|v row at position *pos_dev, then
+ * out_bf16[B, H*64] = softmax(q_pos . K[0..pos]^T / 8) V[0..pos].  The position is read from DEVICE memory so that one
+ * captured CUDA graph serves every step of a generation; advance_counter bumps it at the end of the step.      */
+int b200vit_attn_decode(const void* kv_cache, void* out_bf16, int B, int Nmax, int H, const int* pos_dev, void* stream);
+int b200vit_kv_append(const void* rows_bf16, void* kv_cache, int B, int Nmax, int row_elems, const int* pos_dev, void* stream);
+int b200vit_advance_counter(int* counter, int by, void* stream);
 
 /* ---- fused multi-tensor AdamW + bf16 operand refresh (torch.optim.AdamW at train_vit.py:82,105, ------------
  * train_titok.py:134,160, train_videogpt.py:107,134; arithmetic of torch/optim/adam.py::_single_tensor_adam)

@@ -61,6 +61,14 @@ def test_gemm_forward_family(ops, M, N, K):
     assert_close_bf16(out, ref - b, "gemm_bias_f32", rel=2e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(1, 2304, 768), (16, 2304, 768), (16, 3072, 768), (16, 768, 3072), (17, 1024, 768), (40, 16, 128),
+                                   (64, 776, 256), (3, 10 + 6, 384)])
+def test_gemm_skinny_decode_shapes(ops, M, N, K):
+    # M <= 64 and K % 128 == 0: the weight-streaming mma.sync kernel of the single-token decode step (gemm_skinny.cu);
+    # same contract and tolerances as the tile kernel
+    test_gemm_forward_family(ops, M, N, K)
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 64, 256), (256, 768, 768), (1000, 2304, 768), (788, 3072, 768), (520, 576, 192)])
 def test_gemm_dgrad_and_wgrad(ops, M, N, K):
     rng = np.random.default_rng(M * 3 + N + K)
@@ -482,7 +490,15 @@ def test_attn_decode_against_oracle(ops, B, H, Nmax, pos):
     # one query (the row at `pos`) against the cached keys / values 0..pos: oracle sdpa_fwd on the same bf16 values
     rng = np.random.default_rng(B + H + pos)
     cache = bf16_round(rng.standard_normal((B, Nmax, 3, H, 64)).astype(np.float32))
-    o = ops.attn_decode(to_dev(cache, torch.bfloat16), pos)
+    pos_dev = torch.tensor([pos], device=DEV, dtype=torch.int32)
+    cd = to_dev(cache, torch.bfloat16)
+    # the new token's fused q|k|v row goes in through kv_append (cache row `pos` is garbage before)
+    row = cd[:, pos].reshape(B, -1).clone()
+    cd[:, pos] = 0
+    ops.kv_append(row, cd, pos_dev)
+    o = ops.attn_decode(cd, pos_dev)
+    ops.advance_counter(pos_dev, 1)
+    assert int(pos_dev.item()) == pos + 1
     q = cache[:, pos:pos + 1, 0].transpose(0, 2, 1, 3).astype(np.float64)           # [B, H, 1, 64]
     k = cache[:, :pos + 1, 1].transpose(0, 2, 1, 3).astype(np.float64)
     v = cache[:, :pos + 1, 2].transpose(0, 2, 1, 3).astype(np.float64)

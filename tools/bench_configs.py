@@ -119,6 +119,65 @@ titok_step("configs[2] TiTok-S 256px tokenizer, 32 latent tokens, K=4096: enc + 
 stack_step("configs[2] TiTok-S encoder stack, N=288 (32 latent + 256 patches), batch 256", M.S(block_size=288), 256, 288, False)
 stack_step("configs[4] VideoGPT-B causal stack, N=1024, batch 16", M.B(block_size=1024, causal=True), 16, 1024, True)
 
+class _VideoGPTCfg:   # train_videogpt.VideoGPTConfig (train_videogpt.py:18-28)
+    def __init__(self, frame_size, codebook_size, transformer, max_frames, dropout):
+        self.frame_size, self.codebook_size, self.transformer = frame_size, codebook_size, transformer
+        self.max_frames, self.dropout = max_frames, dropout
+        self.max_tokens = max_frames * frame_size
+        self.trans_config = M.transformer_configs[transformer](block_size=self.max_tokens, dropout=dropout, causal=True)
+        self.n_embd = self.trans_config.n_embd
+
+
+def videogpt_cases(B):
+    """configs[4]: train_videogpt.py:130-134 training step, and generate() (train_videogpt.py:56-65): KV-cached vs the
+    reference's algorithm (whole stack re-run per token) through the same kernels."""
+    import time
+    from b200vit.optim import AdamW
+    torch.manual_seed(0)
+    net = M.VideoGPT(_VideoGPTCfg(64, 1024, "B", 16, 0.0)).to(dev)
+    opt = AdamW(net.parameters(), lr=1e-4)
+    x = torch.randint(0, 1024, (B, 16, 64), device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            _, loss = net(x)
+        loss.backward()
+        opt.step()
+    ms = timeit(step)
+    fl = 3 * (12 * layer_flops(1024, 768, True) + 2 * 1024 * 768 * 1024) * B
+    rows.append((f"configs[4] VideoGPT-B training step (embed + causal stack + vocab proj + CE + bwd + AdamW), N=1024, batch {B}",
+                 f"{ms:.2f} ms/step", f"{B / ms * 1e3:.0f} seq/s", f"{fl / ms / 1e9:.0f} TFLOP/s"))
+    net.eval()
+    prompt = torch.randint(0, 1024, (B, 512), device=dev)
+    n_new = 64
+    net.generate(prompt, 4)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    out = net.generate(prompt, n_new)
+    torch.cuda.synchronize(); t_kv = time.perf_counter() - t0
+
+    def full_recompute(tokens, n):          # the reference's generate(): re-run everything for every token
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(n):
+                sos = torch.full((tokens.shape[0], 1), 1024, device=dev, dtype=torch.long)
+                xx = torch.cat([sos, tokens], dim=-1)
+                hh = net.tok_embed(xx) + net.pos_embed(torch.arange(xx.shape[1], device=dev))
+                lg = net.proj(net.transformer(hh)[:, -1])
+                tokens = torch.cat([tokens, lg.argmax(-1, keepdim=True)], dim=-1)
+        return tokens
+    full_recompute(prompt, 2)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    full_recompute(prompt, n_new)
+    torch.cuda.synchronize(); t_full = time.perf_counter() - t0
+    rows.append((f"configs[4] VideoGPT-B generate: prompt 512 + {n_new} new tokens, batch {B}, KV-cached",
+                 f"{t_kv * 1e3:.1f} ms", f"{B * n_new / t_kv:.0f} tok/s",
+                 f"full re-computation per token (the reference's algorithm, same kernels): {t_full * 1e3:.1f} ms = {t_full / t_kv:.1f}x slower"))
+    del net, opt
+    torch.cuda.empty_cache()
+
+
+videogpt_cases(16)
+
 # VQ lookup: configs[2] (rows = B*32, K = 4096, D = 12) and the repo default (B*256 rows, K = 2048)
 for R, K in ((256 * 32, 4096), (256 * 256, 2048), (16 * 16 * 64, 1024)):
     x = torch.randn(R, 12, device=dev)

@@ -475,15 +475,16 @@ def stack_prefill(x, layers, n_heads, n_max):
 
 
 @torch.no_grad()
-def stack_decode_step(x, layers, caches, pos):
-    """One new token per sequence: x [B, d] fp32 at position `pos`; appends its k, v to the caches, returns [B, d] fp32."""
-    B, d = x.shape
+def stack_decode_step(x, layers, caches, pos_dev):
+    """One new token per sequence: x [B, d] fp32 at position *pos_dev (int32 device scalar); appends its q|k|v row to the
+    caches, returns [B, d] fp32.  Nothing here depends on the position on the host, so the step can be captured once in a
+    CUDA graph and replayed for every generated token."""
     h = _as_rows_f32(x)
     for P, cache in zip(layers, caches):
         a, _, _, _, _ = ops.layernorm_fwd(h)
         qkv = ops.gemm_bias(a, bf16_of(P.qkv_w), _f32c(P.qkv_b))   # [B, 3d]
-        cache[:, pos].copy_(qkv.view(B, 3, cache.shape[3], 64))
-        o = ops.attn_decode(cache, pos)
+        ops.kv_append(qkv, cache, pos_dev)
+        o = ops.attn_decode(cache, pos_dev)
         b, _, _, _, x1 = ops.layernorm_fwd(h, add=o, want_x_out=True)
         g, _ = ops.gemm_bias_gelu(b, bf16_of(P.fc1_w), _f32c(P.fc1_b))
         h = ops.gemm_bias_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1)

@@ -333,17 +333,40 @@ class VideoGPT(nn.Module):
 
         sos = torch.full((B, 1), self.config.codebook_size, device=tokens.device, dtype=torch.long)
         inp = torch.cat([sos, tokens], dim=-1)                                     # [B, T0 + 1]
-        h = Fn.ops.embed_fwd(inp.contiguous(), Fn._f32c(self.tok_embed.weight), Fn._f32c(self.pos_embed.weight), 0)
+        tok_w, pos_w = Fn._f32c(self.tok_embed.weight), Fn._f32c(self.pos_embed.weight)
+        h = Fn.ops.embed_fwd(inp.contiguous(), tok_w, pos_w, 0)
         h, caches = Fn.stack_prefill(h, layers, H, total)
-        new = next_token(h[:, -1])
-        out = [tokens, new]
-        for j in range(1, n):
-            pos = T0 + j                                                           # position of the token generated last
-            x = Fn.ops.embed_fwd(new.contiguous(), Fn._f32c(self.tok_embed.weight), Fn._f32c(self.pos_embed.weight), pos)
-            h1 = Fn.stack_decode_step(x.view(B, -1), layers, caches, pos)
-            new = next_token(h1)
-            out.append(new)
-        return torch.cat(out, dim=-1)
+        out = torch.empty(B, total, device=tokens.device, dtype=torch.long)
+        out[:, :T0] = tokens
+        new = next_token(h[:, -1]).contiguous()                                    # static buffer: the token fed to the next step
+        out[:, T0] = new.view(-1)
+        if n == 1:
+            return out
+        pos_dev = torch.full((1,), T0 + 1, device=tokens.device, dtype=torch.int32)  # position of the token generated last
+
+        def step():   # embeds `new` at *pos_dev, runs the cached stack, leaves the next greedy token in `new`, advances
+            x = Fn.ops.embed_fwd(new, tok_w, pos_w, 0, pos0_dev=pos_dev)
+            h1 = Fn.stack_decode_step(x.view(B, -1), layers, caches, pos_dev)
+            new.copy_(next_token(h1))
+            Fn.ops.advance_counter(pos_dev, 1)
+
+        step()                                                                      # j = 1, eager (also the graph's warm-up)
+        out[:, T0 + 1] = new.view(-1)
+        graph = None
+        if n - 2 >= self.GRAPH_MIN_STEPS:
+            # the step has no host-side dependence on the position: capture it once, replay it per token
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+        for j in range(2, n):
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
+            out[:, T0 + j] = new.view(-1)
+        return out
+
+    GRAPH_MIN_STEPS = 8   # below this many remaining tokens capturing a graph does not pay
 
     def generate_frames(self, video_tokens, n=1):
         tokens = video_tokens.reshape(video_tokens.shape[0], -1)

@@ -275,15 +275,30 @@ def cast_bf16(t, out=None):
 
 
 # ---------------------------------------------------------------- KV-cached decode
-def attn_decode(kv_cache, pos):
-    """kv_cache [B, Nmax, 3, H, 64] bf16 (row `pos` holds the new token's q, k, v) -> o [B, H*64] bf16."""
+def attn_decode(kv_cache, pos_dev):
+    """kv_cache [B, Nmax, 3, H, 64] bf16 whose row *pos_dev holds the new token's q, k, v -> o [B, H*64] bf16.
+    pos_dev: int32 device tensor with one element (the position is read on the device: graph-capturable)."""
     B, Nmax, three, H, hd = kv_cache.shape
     if three != 3 or hd != 64:
         raise ValueError("attn_decode: cache must be [B, Nmax, 3, H, 64]")
     out = torch.empty(B, H * 64, device=kv_cache.device, dtype=BF16)
-    _call("b200vit_attn_decode", kv_cache, ptr(_chk(kv_cache, BF16, "kv_cache")), ptr(out), B, Nmax, H, pos, stream_ptr(),
-          hbm_bytes=float(B * H * (pos + 1) * 256))
+    _call("b200vit_attn_decode", kv_cache, ptr(_chk(kv_cache, BF16, "kv_cache")), ptr(out), B, Nmax, H, ptr(_chk(pos_dev, torch.int32, "pos")),
+          stream_ptr())
     return out
+
+
+def kv_append(rows, kv_cache, pos_dev):
+    """kv_cache[:, *pos_dev] = rows ([B, 3*H*64] bf16: the fused QKV projection of the new token)."""
+    B, Nmax = kv_cache.shape[0], kv_cache.shape[1]
+    row_elems = kv_cache.shape[2] * kv_cache.shape[3] * kv_cache.shape[4]
+    if rows.numel() != B * row_elems:
+        raise ValueError("kv_append: rows must be [B, 3*H*64]")
+    _call("b200vit_kv_append", rows, ptr(_chk(rows, BF16, "rows")), ptr(_chk(kv_cache, BF16, "kv_cache")), B, Nmax, row_elems,
+          ptr(_chk(pos_dev, torch.int32, "pos")), stream_ptr())
+
+
+def advance_counter(counter, by=1):
+    _call("b200vit_advance_counter", counter, ptr(_chk(counter, torch.int32, "counter")), by, stream_ptr())
 
 
 # ---------------------------------------------------------------- classifier head + cross-entropy
@@ -316,15 +331,16 @@ def depatchify_fwd(rows, w_cmajor, bias_cmajor, B, Ht, Wt, p, C):
     return img
 
 
-def embed_fwd(idx, tok_embed, pos_embed, pos0=0):
-    """idx [B, S] int64 -> fp32 [B, S, d] = tok_embed[idx] + pos_embed[pos0 : pos0 + S] (train_videogpt.py:50)."""
+def embed_fwd(idx, tok_embed, pos_embed, pos0=0, pos0_dev=None):
+    """idx [B, S] int64 -> fp32 [B, S, d] = tok_embed[idx] + pos_embed[pos0 : pos0 + S] (train_videogpt.py:50).
+    pos0_dev (int32 device tensor) overrides pos0 with a position read on the device (graph-captured decode)."""
     B, S = idx.shape
     V, d = tok_embed.shape
-    if pos0 + S > pos_embed.shape[0]:
+    if pos0_dev is None and pos0 + S > pos_embed.shape[0]:
         raise ValueError(f"embed_fwd: positions {pos0}..{pos0 + S - 1} exceed pos_embed ({pos_embed.shape[0]} rows)")
     out = torch.empty(B, S, d, device=tok_embed.device, dtype=F32)
     _call("b200vit_embed_fwd", tok_embed, ptr(_chk(idx, torch.int64, "idx")), ptr(_chk(tok_embed, F32, "tok_embed")),
-          ptr(_chk(pos_embed, F32, "pos_embed")), ptr(out), B, S, d, pos0, V, stream_ptr())
+          ptr(_chk(pos_embed, F32, "pos_embed")), ptr(out), B, S, d, pos0, ptr(pos0_dev), pos_embed.shape[0], V, stream_ptr())
     return out
 
 

@@ -119,9 +119,20 @@ int gemm_depatch_epilogue(const void* rows_bf16, const void* w, const float* bia
   return launch_bn<false, false, EPI_DEPATCH_F32>(rows_bf16, K, w, K, rows, N, K, ep, false, st);
 }
 
+// gemm_skinny.cu: weight-streaming kernel for M <= 64 (the single-token decode step); 1 = launched, 0 = not applicable
+int gemm_skinny_try(int kind, const void* x, const void* w, const float* bias, void* out, void* out2, const float* resid,
+                    int M, int N, int K, cudaStream_t st);
+
 }  // namespace b200
 
 using namespace b200;
+
+#define B200_TRY_SKINNY(kind, out, out2, resid)                                                            \
+  do {                                                                                                     \
+    const int _sk = gemm_skinny_try(kind, x, w, bias, out, out2, resid, M, N, K, (cudaStream_t)stream);    \
+    if (_sk < 0) return _sk;                                                                               \
+    if (_sk == 1) return OK;                                                                               \
+  } while (0)
 
 extern "C" {
 
@@ -148,6 +159,7 @@ int b200vit_gemm_bias(const void* x, const void* w, const float* bias, void* y, 
                       void* stream) {
   int rc = check_common(x, w, y, M, N, K);
   if (rc) return rc;
+  B200_TRY_SKINNY(EPI_BF16, y, nullptr, nullptr);
   EpiParams ep = make_ep(y, N);
   ep.bias = bias;
   return launch_bn<false, false, EPI_BF16>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
@@ -158,6 +170,7 @@ int b200vit_gemm_bias_gelu(const void* x, const void* w, const float* bias, void
   int rc = check_common(x, w, g, M, N, K);
   if (rc) return rc;
   B200_REQUIRE(gprime != nullptr, "gemm_bias_gelu: gprime is null");
+  B200_TRY_SKINNY(EPI_GELU_BF16, g, gprime, nullptr);
   EpiParams ep = make_ep(g, N);
   ep.bias = bias;
   return launch_bn<false, false, EPI_GELU_BF16>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream, gprime);
@@ -168,6 +181,7 @@ int b200vit_gemm_bias_residual(const void* x, const void* w, const float* bias, 
   int rc = check_common(x, w, out, M, N, K);
   if (rc) return rc;
   B200_REQUIRE(resid != nullptr, "gemm_bias_residual: resid is null");
+  B200_TRY_SKINNY(EPI_RESID_F32, out, nullptr, resid);
   EpiParams ep = make_ep(out, N);
   ep.bias = bias; ep.aux = resid; ep.ldaux = N;
   return launch_bn<false, false, EPI_RESID_F32>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);
@@ -190,6 +204,7 @@ int b200vit_gemm_bias_f32(const void* x, const void* w, const float* bias, float
                           int K, void* stream) {
   int rc = check_common(x, w, out, M, N, K);
   if (rc) return rc;
+  B200_TRY_SKINNY(EPI_F32, out, nullptr, nullptr);
   EpiParams ep = make_ep(out, N);
   ep.bias = bias;
   return launch_bn<false, false, EPI_F32>(x, K, w, K, M, N, K, ep, false, (cudaStream_t)stream);

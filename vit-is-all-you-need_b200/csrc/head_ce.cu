@@ -212,7 +212,9 @@ namespace b200 {
 
 __global__ void __launch_bounds__(256)
 embed_fwd_kernel(const long long* __restrict__ idx, const float* __restrict__ tok, const float* __restrict__ pos,
-                 float* __restrict__ out, long long rows, int S, int d, int pos0, int vocab) {
+                 float* __restrict__ out, long long rows, int S, int d, int pos0, const int* __restrict__ pos0_dev, int n_pos,
+                 int vocab) {
+  if (pos0_dev != nullptr) pos0 = min(max(__ldg(pos0_dev), 0), n_pos - S);   // decode: the position lives on the device
   const int per_row = d >> 2;
   const long long total = rows * per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -260,14 +262,16 @@ embed_bwd_pos_kernel(const float* __restrict__ dy, float* __restrict__ dpos, int
 extern "C" {
 
 int b200vit_embed_fwd(const long long* idx, const float* tok_embed, const float* pos_embed, float* out, int B, int S, int d,
-                      int pos0, int vocab, void* stream) {
-  B200_REQUIRE(idx && tok_embed && pos_embed && out && B > 0 && S > 0 && d > 0 && d % 4 == 0 && pos0 >= 0 && vocab > 0,
-               "embed_fwd: bad arguments (d must be a multiple of 4)");
+                      int pos0, const int* pos0_dev, int n_pos, int vocab, void* stream) {
+  B200_REQUIRE(idx && tok_embed && pos_embed && out && B > 0 && S > 0 && d > 0 && d % 4 == 0 && pos0 >= 0 && vocab > 0 &&
+                   n_pos >= S && (pos0_dev != nullptr || pos0 + S <= n_pos),
+               "embed_fwd: bad arguments (d must be a multiple of 4, positions within pos_embed)");
   const long long total = (long long)B * S * (d / 4);
   const long long want = (total + 255) / 256;
   const int cap = b200::num_sms() * 16;
   b200::embed_fwd_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(idx, tok_embed, pos_embed, out,
-                                                                                         (long long)B * S, S, d, pos0, vocab);
+                                                                                         (long long)B * S, S, d, pos0, pos0_dev, n_pos,
+                                                                                         vocab);
   B200_CUDA(cudaGetLastError());
   return b200::OK;
 }
