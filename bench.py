@@ -132,19 +132,41 @@ def numpy_vit_b_params(rng):
 
 
 def cpu_reference_step_rate(batch, steps, warmup):
-    """The reference's CPU implementation of the path == the numpy oracle port (fwd + CE + bwd, fp32, all host
-    threads through the BLAS numpy links).  Returns (images/s, seconds per step)."""
+    """The reference's CPU implementation of the path == the numpy oracle port (fwd + CE + bwd + AdamW, fp32, all host
+    threads through the BLAS numpy links): the same step the GPU arm times.  Returns (images/s, seconds per step)."""
     import numpy as np
+    from oracle import adamw_oracle as A
     from oracle import vit_oracle as O
     rng = np.random.default_rng(0)
     P = numpy_vit_b_params(rng)
     x = rng.standard_normal((batch, 3, IMAGE, IMAGE)).astype(np.float32)
     labels = rng.integers(0, CLASSES, size=(batch,))
+
+    def leaves(tree):   # (container, key) of every parameter array, in a fixed order
+        out = [(tree, k) for k in ("conv_w", "conv_b", "pos_emb", "extra_emb", "head_w", "head_b")]
+        for layer in tree["layers"]:
+            out += [(layer, k) for k in ("qkv_w", "qkv_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+        return out
+
+    state = {}
+    n_done = [0]
+
+    def one_step():
+        _, _, g = O.vit_classifier_loss_and_grads(x, labels, P, HEADS)
+        n_done[0] += 1
+        for i, ((pc, k), (gc, _)) in enumerate(zip(leaves(P), leaves(g))):
+            m, v = state.get(i, (None, None))
+            if m is None:
+                m, v = np.zeros_like(pc[k]), np.zeros_like(pc[k])
+            grad = np.asarray(gc[k], dtype=np.float32).reshape(pc[k].shape)
+            pc[k], m, v, _ = A.adamw_step(pc[k], grad, m, v, n_done[0], 1e-4, weight_decay=1e-2)
+            state[i] = (m, v)
+
     for _ in range(warmup):
-        O.vit_classifier_loss_and_grads(x, labels, P, HEADS)
+        one_step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.vit_classifier_loss_and_grads(x, labels, P, HEADS)
+        one_step()
     dt = (time.perf_counter() - t0) / steps
     return batch / dt, dt
 
@@ -162,10 +184,10 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ViT-B/16 224px train step (fwd+CE+bwd), reference CPU path (numpy oracle port)",
+        "config": {"workload": "ViT-B/16 224px train step (fwd + CE + bwd + AdamW), reference CPU path (numpy oracle port)",
                    "global_batch": batch, "parallelism": "cpu"},
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} step(s) of batch {batch} (ViT-B/16 224, fwd+CE+bwd, fp32 numpy/BLAS)"},
+                         "sample": f"{steps} step(s) of batch {batch} (ViT-B/16 224, fwd+CE+bwd+AdamW, fp32 numpy/BLAS)"},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -347,7 +369,7 @@ def run_gpu_arm(args):
         cb = args.cpu_batch
         cips, cdt = cpu_reference_step_rate(cb, 1, 0)
         line["cpu_baseline"] = {"value": cips, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"1 step of batch {cb} (ViT-B/16 224, fwd+CE+bwd, fp32 numpy oracle, {cdt:.1f} s)"}
+                                "sample": f"1 step of batch {cb} (ViT-B/16 224, fwd+CE+bwd+AdamW, fp32 numpy oracle, {cdt:.1f} s)"}
     print(json.dumps(line), flush=True)
     return 0
 
