@@ -448,3 +448,30 @@ def test_embed_fwd_bwd(golden_dir):
     np.add.at(ref_tok, idx.reshape(-1), dy.reshape(-1, d).astype(np.float64))
     np.testing.assert_allclose(dtok.cpu().numpy(), ref_tok, rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(dpos.cpu().numpy(), dy.astype(np.float64).sum(0), rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ UViTBlock
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_uvit_block_matches_reference(golden_dir, tag):
+    """blocks.UViTBlock (blocks.py:174-201): batch-first block, qkv bias optional, optional skip_linear over cat([x, skip])."""
+    from b200vit import modules as M
+    g = np.load(os.path.join(golden_dir, "uvit.npz"))
+    dim, heads, B, L, qkv_bias, skip = (int(v) for v in g[f"{tag}_cfg"])
+    m = M.UViTBlock(dim, heads, qkv_bias=bool(qkv_bias), skip=bool(skip))
+    assert list(m.state_dict().keys()) == [str(k) for k in g[f"{tag}_keys"]]
+    m = _det_weights_like_golden(m, seed=61 + L)          # tests/golden/make_golden.py:gen_uvit
+    with torch.no_grad():
+        m.norm1.weight.add_(1.0)
+        m.norm2.weight.add_(1.0)
+    m = m.to(DEV)
+    x = torch.from_numpy(g[f"{tag}_x"]).to(DEV).requires_grad_(True)
+    sk = torch.from_numpy(g[f"{tag}_skip"]).to(DEV).requires_grad_(True) if skip else None
+    y = m(x, sk)
+    assert y.shape == x.shape and y.dtype == torch.float32
+    assert rel_l2(y.detach().cpu().numpy(), g[f"{tag}_y"]) < 1e-2
+    y.backward(torch.from_numpy(g[f"{tag}_dy"]).to(DEV))
+    check_grad(x.grad, g[f"{tag}_dx"], "dx")
+    if skip:
+        check_grad(sk.grad, g[f"{tag}_dskip"], "dskip")
+    for k, p in m.named_parameters():
+        check_grad(p.grad, g[f"{tag}_g_{k}"], k)

@@ -5,6 +5,6 @@ Public surface mirrors the reference (SnakeOnex/vit-is-all-you-need): see module
 by their original bare module names.
 """
 from .modules import (Attention, B, CrossEntropyLoss, L, PatchConv2d, Quantizer, ResidualAttentionBlock, S, Transformer, TransformerConfig,  # noqa: F401
-                      TiTok, TiTokDecoder, TiTokEncoder, TransformerLayer, VectorQuantizer, VideoGPT, ViT, ViTClassifier, ViTConfig, transformer_configs)
+                      TiTok, TiTokDecoder, TiTokEncoder, TransformerLayer, UViTBlock, VectorQuantizer, VideoGPT, ViT, ViTClassifier, ViTConfig, transformer_configs)
 
 __version__ = "0.1.0"

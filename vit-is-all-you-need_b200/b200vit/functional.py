@@ -537,16 +537,20 @@ class CrossEntropyFn(torch.autograd.Function):
 
 # ------------------------------------------------------------------------------------------------------------
 # blocks.ResidualAttentionBlock (blocks.py:32-70): affine LN, MHA (in_proj + out_proj), [L, B, d] layout
+# blocks.UViTBlock (blocks.py:174-201): the same block batch-first ([B, L, d]), QKV bias optional
 # ------------------------------------------------------------------------------------------------------------
 class ResidualAttentionBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, n_heads, has_mlp, ln1_w, ln1_b, in_w, in_b, out_w, out_b, *mlp):
-        L, B, d = x.shape
+    def forward(ctx, x, n_heads, has_mlp, batch_first, ln1_w, ln1_b, in_w, in_b, out_w, out_b, *mlp):
+        if batch_first:
+            B, L, d = x.shape
+        else:
+            L, B, d = x.shape
         M = L * B
         x0 = _as_rows_f32(x).view(M, d)
         a, _, mean1, rstd1, _ = ops.layernorm_fwd(x0, gamma=_f32c(ln1_w), beta=_f32c(ln1_b))
         qkv = ops.gemm_bias(a, bf16_of(in_w), _f32c(in_b))
-        o, lse = ops.flash_attn_fwd(qkv, B, L, n_heads, False, seq_first=True)
+        o, lse = ops.flash_attn_fwd(qkv, B, L, n_heads, False, seq_first=not batch_first)
         o2 = o.view(M, d)
         x1 = ops.gemm_bias_residual(o2, bf16_of(out_w), _f32c(out_b), x0)
         saved = [x0, mean1, rstd1, a, qkv, o, lse, x1]
@@ -559,12 +563,12 @@ class ResidualAttentionBlockFn(torch.autograd.Function):
             saved += [mean2, rstd2, b, u, g]
         ctx.saved = saved
         ctx.params = (ln1_w, in_w, out_w) + tuple(mlp)
-        ctx.dims = (L, B, d, n_heads, has_mlp)
-        return y.view(L, B, d)
+        ctx.dims = (L, B, d, n_heads, has_mlp, batch_first, tuple(x.shape), in_b is not None)
+        return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
-        L, B, d, H, has_mlp = ctx.dims
+        L, B, d, H, has_mlp, batch_first, xshape, has_in_b = ctx.dims
         M = L * B
         s = ctx.saved
         x0, mean1, rstd1, a, qkv, o, lse, x1 = s[:8]
@@ -586,13 +590,14 @@ class ResidualAttentionBlockFn(torch.autograd.Function):
             dx1, dx1_16 = dx2, ops.cast_bf16(dx2)
         d_out_w, d_out_b = ops.gemm_wgrad(dx1_16, o.view(M, d), want_bias=True)
         do = ops.gemm_dgrad(dx1_16, bf16_of(out_w))
-        dqkv = ops.flash_attn_bwd(qkv, o, do.view(L, B, d), lse, B, L, H, False, seq_first=True).view(M, -1)
+        dqkv = ops.flash_attn_bwd(qkv, o, do.view(xshape), lse, B, L, H, False, seq_first=not batch_first).view(M, -1)
         d_in_w, d_in_b = ops.gemm_wgrad(dqkv, a, want_bias=True)
         da = ops.gemm_dgrad(dqkv, bf16_of(in_w))
         dx0, _, d_ln1_w, d_ln1_b = ops.layernorm_bwd(da, x0, mean1, rstd1, gamma=_f32c(ln1_w), dres=dx1,
                                                      want_bf16=False, affine_grads=True)
         ctx.saved = None
-        return (dx0.view(L, B, d), None, None, d_ln1_w, d_ln1_b, d_in_w, d_in_b, d_out_w, d_out_b, *mlp_grads)
+        return (dx0.view(xshape), None, None, None, d_ln1_w, d_ln1_b, d_in_w, (d_in_b if has_in_b else None), d_out_w, d_out_b,
+                *mlp_grads)
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -401,9 +401,68 @@ class ResidualAttentionBlock(nn.Module):
         if self.mlp_ratio > 0:
             mlp = (self.ln_2.weight, self.ln_2.bias, self.mlp.c_fc.weight, self.mlp.c_fc.bias,
                    self.mlp.c_proj.weight, self.mlp.c_proj.bias)
-        return Fn.ResidualAttentionBlockFn.apply(x, self.n_head, self.mlp_ratio > 0, self.ln_1.weight, self.ln_1.bias,
+        return Fn.ResidualAttentionBlockFn.apply(x, self.n_head, self.mlp_ratio > 0, False, self.ln_1.weight, self.ln_1.bias,
                                                  self.attn.in_proj_weight, self.attn.in_proj_bias,
                                                  self.attn.out_proj.weight, self.attn.out_proj.bias, *mlp)
+
+
+class _UViTAttention(nn.Module):
+    """Parameter container with the names of blocks.Attention (blocks.py:84-93): qkv (bias optional), proj."""
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0.0, proj_drop=0.0):
+        super().__init__()
+        if qk_scale is not None or attn_drop != 0.0 or proj_drop != 0.0:
+            raise NotImplementedError("b200vit UViTBlock implements qk_scale=None and zero attention / projection dropout")
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+
+
+class _UViTMlp(nn.Module):
+    """Parameter container with the names of blocks.Mlp (blocks.py:157-171): fc1, act, fc2, drop."""
+
+    def __init__(self, in_features, hidden_features, drop=0.0):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_features, in_features)
+        self.drop = nn.Dropout(drop)
+
+
+class UViTBlock(nn.Module):
+    """blocks.UViTBlock (blocks.py:174-201): batch-first pre-norm block x + attn(norm1(x)); x + mlp(norm2(x)) with an
+    optional skip_linear over cat([x, skip]).  Same parameter names / state_dict keys (norm1, attn.qkv, attn.proj, norm2,
+    mlp.fc1, mlp.fc2, skip_linear); runs on the kernels of ResidualAttentionBlock with the batch-first attention layout.
+    Dropout, drop-path and activation checkpointing are not implemented (the reference never instantiates this block)."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, qkv_bias=False, qk_scale=None, drop=0.0, attn_drop=0.0, drop_path=0.0,
+                 act_layer=nn.GELU, norm_layer=nn.LayerNorm, skip=False, use_checkpoint=False):
+        super().__init__()
+        if act_layer is not nn.GELU or norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("b200vit UViTBlock implements nn.GELU + nn.LayerNorm only")
+        if drop != 0.0 or drop_path != 0.0 or use_checkpoint:
+            raise NotImplementedError("b200vit UViTBlock implements drop = drop_path = 0 and use_checkpoint=False")
+        if dim // num_heads != 64:
+            raise NotImplementedError("b200vit attention kernels are built for head_dim 64")
+        self.norm1 = norm_layer(dim)
+        self.attn = _UViTAttention(dim, num_heads=num_heads, qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop,
+                                   proj_drop=drop)
+        self.drop_path = nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = _UViTMlp(dim, int(dim * mlp_ratio), drop=drop)
+        self.skip_linear = nn.Linear(2 * dim, dim) if skip else None
+        self.use_checkpoint = use_checkpoint
+
+    def forward(self, x, skip=None):
+        if self.skip_linear is not None:
+            x = Fn.LinearFn.apply(torch.cat([x, skip], dim=-1), self.skip_linear.weight, self.skip_linear.bias, False)
+        return Fn.ResidualAttentionBlockFn.apply(x, self.attn.num_heads, True, True, self.norm1.weight, self.norm1.bias,
+                                                 self.attn.qkv.weight, self.attn.qkv.bias, self.attn.proj.weight,
+                                                 self.attn.proj.bias, self.norm2.weight, self.norm2.bias,
+                                                 self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias)
 
 
 class VectorQuantizer(nn.Module):

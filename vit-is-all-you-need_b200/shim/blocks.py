@@ -1,8 +1,8 @@
 """Drop-in for the reference's top-level module `blocks`.
 
-The hot-path classes (ResidualAttentionBlock blocks.py:32-70, VectorQuantizer blocks.py:405-505) come from
+The hot-path classes (ResidualAttentionBlock blocks.py:32-70, UViTBlock blocks.py:174-201, VectorQuantizer blocks.py:405-505) come from
 b200vit.modules; everything else the reference's blocks.py defines (TiTokEncoder / TiTokDecoder blocks.py:208-361,
-UViTBlock, ...) is taken from the reference's own file, executed in this module's namespace, so that
+...) is taken from the reference's own file, executed in this module's namespace, so that
 `from blocks import TiTokEncoder, TiTokDecoder, VectorQuantizer` (train_tatitok.py:13) keeps working and the encoder /
 decoder assemble themselves out of the sm_100a-backed blocks (they look `ResidualAttentionBlock` up by its module-global
 name when they are constructed)."""
@@ -10,6 +10,7 @@ import os
 import sys
 
 from b200vit.modules import ResidualAttentionBlock as _RAB
+from b200vit.modules import UViTBlock as _UVB
 from b200vit.modules import VectorQuantizer as _VQ
 
 _here = os.path.dirname(os.path.abspath(__file__))
@@ -22,3 +23,4 @@ for _p in sys.path:
 
 ResidualAttentionBlock = _RAB
 VectorQuantizer = _VQ
+UViTBlock = _UVB
