@@ -35,3 +35,17 @@ def test_init_fails_loudly_without_gpu():
     lib = _cabi.load()
     assert lib.b200vit_init(ctypes.c_int(0)) != 0
     assert len(lib.b200vit_last_error()) > 0
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under vit-is-all-you-need_b200/ may import or execute it."""
+    import glob
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vit-is-all-you-need_b200")
+    offenders = []
+    for path in glob.glob(os.path.join(root, "**", "*.py"), recursive=True):
+        for n, line in enumerate(open(path), 1):
+            if re.search(r"^\s*(from|import)\s+oracle\b", line) or "oracle/" in line and "subprocess" in line:
+                offenders.append(f"{path}:{n}")
+    assert not offenders, offenders
