@@ -475,3 +475,26 @@ def test_uvit_block_matches_reference(golden_dir, tag):
         check_grad(sk.grad, g[f"{tag}_dskip"], "dskip")
     for k, p in m.named_parameters():
         check_grad(p.grad, g[f"{tag}_g_{k}"], k)
+
+
+@pytest.mark.parametrize("B,T0,n", [(1, 0, 3), (2, 1, 1), (1, 7, 2), (3, 30, 2)])
+def test_videogpt_generate_edge_shapes(golden_dir, B, T0, n):
+    """Empty prompt (only the SOS token is prefilled), a single new token, batch 1, and the last position of the block."""
+    model, g = _videogpt(golden_dir, 53, 0.3)
+    model.eval()
+    rng = np.random.default_rng(B + T0)
+    prompt = torch.from_numpy(rng.integers(0, 32, size=(B, T0))).to(DEV)
+    out = model.generate(prompt, n)
+    assert out.shape == (B, T0 + n) and torch.equal(out[:, :T0], prompt)
+    assert int(out.min()) >= 0 and int(out.max()) < 32
+    # the first generated token equals the arg-max of the training-path logits at the last prefilled position
+    with torch.no_grad():
+        sos = torch.full((B, 1), model.config.codebook_size, device=DEV, dtype=torch.long)
+        xx = torch.cat([sos, prompt], dim=-1)
+        hh = model.tok_embed(xx) + model.pos_embed(torch.arange(xx.shape[1], device=DEV))
+        lg = model.proj(model.transformer(hh)[:, -1].float())
+    top2 = torch.topk(lg, 2, dim=-1).values
+    sure = (top2[:, 0] - top2[:, 1]) > 0.75
+    assert torch.equal(out[sure, T0], lg.argmax(-1)[sure])
+    with pytest.raises(ValueError):
+        model.generate(prompt, 32 - T0 + 1)               # would exceed max_tokens = 32 positions

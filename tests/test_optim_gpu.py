@@ -159,3 +159,27 @@ def test_adamw_full_model_matches_torch():
         ref.step()
         for (name, p), q in zip(net.named_parameters(), twin.parameters()):
             _close(p, q.detach().cpu().numpy(), f"{name} after step {step + 1}", rtol=5e-6, scale_atol=5e-7)
+
+
+def test_adamw_skips_parameters_without_gradients_and_handles_changing_sets():
+    """torch semantics: parameters whose .grad is None are left alone; the set may change from step to step."""
+    from b200vit.optim import AdamW
+    rng = np.random.default_rng(8)
+    a0, b0 = rng.standard_normal(300).astype(np.float32), rng.standard_normal((7, 9)).astype(np.float32)
+    a, b = torch.nn.Parameter(torch.from_numpy(a0).to(DEV)), torch.nn.Parameter(torch.from_numpy(b0).to(DEV))
+    opt = AdamW([a, b], lr=1e-2)
+    ga = rng.standard_normal(300).astype(np.float32)
+    a.grad = torch.from_numpy(ga).to(DEV)
+    opt.step()                                            # b has no gradient
+    assert torch.equal(b.detach().cpu(), torch.from_numpy(b0)) and len(opt.state[b]) == 0
+    z = np.zeros_like(a0)
+    a1, m1, v1, _ = A.adamw_step(a0, ga, z, z, 1, 1e-2)
+    _close(a, a1, "a after step 1")
+    gb = rng.standard_normal((7, 9)).astype(np.float32)
+    b.grad = torch.from_numpy(gb).to(DEV)
+    a.grad = None
+    opt.step()                                            # now only b steps (its first step)
+    _close(a, a1, "a untouched in step 2")
+    b1, _, _, _ = A.adamw_step(b0, gb, np.zeros_like(b0), np.zeros_like(b0), 1, 1e-2)
+    _close(b, b1, "b after its first step")
+    assert float(opt.state[a]["step"]) == 1.0 and float(opt.state[b]["step"]) == 1.0

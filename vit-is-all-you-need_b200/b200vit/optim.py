@@ -110,57 +110,71 @@ class AdamW(torch.optim.Optimizer):
                 if p.grad.is_sparse:
                     raise RuntimeError("AdamW does not support sparse gradients")
             device_step = bool(group["capturable"]) or found_inf is not None
-            tab = self._group_tables(gi, group, params)
-            rec = np.empty((len(params), _REC), dtype=np.int64)
-            caches = []
-            for i, p in enumerate(params):
-                st = self._init_state(p, device_step)
-                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                cached = getattr(p, "_b200_bf16", None)
-                w16 = cached[1] if cached is not None and cached[1].shape == p.shape and cached[1].is_contiguous() else None
-                if w16 is not None:
-                    caches.append((p, w16))
-                rec[i] = (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
-                          0 if w16 is None else w16.data_ptr(), p.numel())
-                if g is not p.grad:
-                    caches.append((None, g))  # keep the contiguous copy alive until the launch below
-            key = rec.tobytes()
-            if tab["last"] != key:
-                # a fresh pinned staging block per upload: the caching host allocator does not hand it out again before
-                # the asynchronous copy has run, so a later step cannot overwrite records an earlier copy still needs
-                staging = torch.from_numpy(rec).pin_memory()
-                tab["dev"].copy_(staging, non_blocking=True)
-                tab["last"] = key
-                if torch.cuda.is_current_stream_capturing():
-                    # the copy became a graph node that re-reads this host block at every replay: keep it alive
-                    tab.setdefault("captured_staging", []).append(staging)
-            # step counter: the parameters of a group always step together -> one counter; every state["step"] of
-            # the group tracks it (host tensors are rewritten below, device tensors alias the shared one)
-            step_host, step_dev = 0, None
             if device_step:
-                shared = tab["shared_step"]
-                if shared is None:
-                    first = self.state[params[0]]["step"]
-                    shared = first.to(params[0].device, torch.float32).clone()
-                    tab["shared_step"] = shared
-                for p in params:
-                    self.state[p]["step"] = shared
-                step_dev = shared
+                subsets = [params]          # one device counter per group (documented: the group steps together)
             else:
-                step_host = int(self.state[params[0]]["step"].item()) + 1
-            beta1, beta2 = group["betas"]
-            nbytes = sum(p.numel() * (28 + (2 if r[4] else 0)) for p, r in zip(params, rec))
-            P = _cabi.ptr
-            ops._call("b200vit_adamw_step", params[0], P(tab["dev"]), P(tab["chunks"]), tab["n_chunks"],
-                      float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
-                      step_host, P(step_dev), P(grad_scale), P(found_inf), ops.stream_ptr(), hbm_bytes=float(nbytes))
-            if not device_step:
+                # torch keeps a step count per parameter: parameters that joined later (their .grad was None before) have
+                # their own bias corrections -> one launch per distinct step count (a single launch in the usual case)
+                by_step = {}
                 for p in params:
-                    self.state[p]["step"].fill_(step_host)
-            for p, w16 in caches:
-                if p is not None:
-                    p._b200_bf16 = (Fn.bf16_key(p), w16)   # the operand is current again
+                    st = self.state[p]
+                    by_step.setdefault(int(st["step"].item()) if len(st) else 0, []).append(p)
+                subsets = [by_step[k] for k in sorted(by_step)]
+            for si, subset in enumerate(subsets):
+                self._step_subset((gi, si), group, subset, device_step, grad_scale, found_inf)
         return loss
+
+    def _step_subset(self, gi, group, params, device_step, grad_scale, found_inf):
+        tab = self._group_tables(gi, group, params)
+        rec = np.empty((len(params), _REC), dtype=np.int64)
+        caches = []
+        for i, p in enumerate(params):
+            st = self._init_state(p, device_step)
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            cached = getattr(p, "_b200_bf16", None)
+            w16 = cached[1] if cached is not None and cached[1].shape == p.shape and cached[1].is_contiguous() else None
+            if w16 is not None:
+                caches.append((p, w16))
+            rec[i] = (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                      0 if w16 is None else w16.data_ptr(), p.numel())
+            if g is not p.grad:
+                caches.append((None, g))  # keep the contiguous copy alive until the launch below
+        key = rec.tobytes()
+        if tab["last"] != key:
+            # a fresh pinned staging block per upload: the caching host allocator does not hand it out again before
+            # the asynchronous copy has run, so a later step cannot overwrite records an earlier copy still needs
+            staging = torch.from_numpy(rec).pin_memory()
+            tab["dev"].copy_(staging, non_blocking=True)
+            tab["last"] = key
+            if torch.cuda.is_current_stream_capturing():
+                # the copy became a graph node that re-reads this host block at every replay: keep it alive
+                tab.setdefault("captured_staging", []).append(staging)
+        # step counter: the parameters of a group always step together -> one counter; every state["step"] of
+        # the group tracks it (host tensors are rewritten below, device tensors alias the shared one)
+        step_host, step_dev = 0, None
+        if device_step:
+            shared = tab["shared_step"]
+            if shared is None:
+                first = self.state[params[0]]["step"]
+                shared = first.to(params[0].device, torch.float32).clone()
+                tab["shared_step"] = shared
+            for p in params:
+                self.state[p]["step"] = shared
+            step_dev = shared
+        else:
+            step_host = int(self.state[params[0]]["step"].item()) + 1
+        beta1, beta2 = group["betas"]
+        nbytes = sum(p.numel() * (28 + (2 if r[4] else 0)) for p, r in zip(params, rec))
+        P = _cabi.ptr
+        ops._call("b200vit_adamw_step", params[0], P(tab["dev"]), P(tab["chunks"]), tab["n_chunks"],
+                  float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
+                  step_host, P(step_dev), P(grad_scale), P(found_inf), ops.stream_ptr(), hbm_bytes=float(nbytes))
+        if not device_step:
+            for p in params:
+                self.state[p]["step"].fill_(step_host)
+        for p, w16 in caches:
+            if p is not None:
+                p._b200_bf16 = (Fn.bf16_key(p), w16)   # the operand is current again
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
