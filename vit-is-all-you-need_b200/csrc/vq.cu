@@ -246,13 +246,15 @@ static int launch_vq_fwd(const float* x, const float* codebook, const float* eha
                          cudaStream_t st) {
   constexpr int STRIDE = (DP % 8 == 4) ? DP : DP + 4;
   const size_t per_code = (size_t)STRIDE * 4 + 4;
-  const size_t budget = 200 * 1024;
+  // 4096 codes x (12 floats + norm) = 213 KB: the whole TiTok codebook in ONE chunk (a 200 KB budget split it into
+  // 3936 + 160 codes, the second chunk leaving most lanes idle between two extra barriers)
+  const size_t budget = 216 * 1024;
   int KC = (int)(budget / per_code);
   if (KC > L.K) KC = L.K;
   KC = (KC + 3) & ~3;  // keep s_ee 16-byte aligned after the code rows
   const size_t smem = (size_t)KC * per_code + 16;
   auto kern = vq_fwd_kernel<DP, ROWS>;
-  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(212 * 1024)));
+  B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
   kern<<<grid, VQ_THREADS, smem, st>>>(x, codebook, ehat, ee, L, KC, idx, q, partial);
   B200_CUDA(cudaGetLastError());
   return OK;
@@ -290,14 +292,25 @@ int b200vit_vq_fwd(const float* x, const float* codebook, long long R, int D, in
   VqLayout L{R, D, K, inner, elem_stride, outer_stride, flags};
   vq_prep_kernel<<<(K + 127) / 128, 128, 0, st>>>(codebook, K, D, DP, flags & 1, ehat, ee);
   B200_CUDA(cudaGetLastError());
-  const int rpc = vq_rows_per_cta(DP);
+  int rpc = vq_rows_per_cta(DP);
+  // When the codebook fills an SM's shared memory (K = 4096: 213 KB, one CTA per SM whatever the register count) and
+  // 4 rows per warp would need more than one wave of CTAs, give each warp 8 rows: half the CTAs, half the codebook
+  // staging traffic, twice the independent FMA chains per lane (66 -> 57 us at rows 8192, K 4096).  With smaller
+  // codebooks two CTAs share an SM at 4 rows per warp and the 182-register 8-row variant measured slower
+  // (K 2048, rows 65536: 166 -> 200 us), so it is not used there.  Same arithmetic per (row, code): bit-exact indices.
+  const int stride = (DP % 8 == 4) ? DP : DP + 4;
+  const bool one_cta_per_sm = (size_t)K * (stride * 4 + 4) > 113 * 1024;
+  const bool rows8 = DP <= 16 && DP >= 12 && one_cta_per_sm && (R + rpc - 1) / rpc > num_sms();
+  if (rows8) rpc *= 2;
   const int grid = (int)((R + rpc - 1) / rpc);
   int rc;
   switch (DP) {
     case 4:  rc = launch_vq_fwd<4, 4>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st); break;
     case 8:  rc = launch_vq_fwd<8, 4>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st); break;
-    case 12: rc = launch_vq_fwd<12, 4>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st); break;
-    case 16: rc = launch_vq_fwd<16, 4>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st); break;
+    case 12: rc = rows8 ? launch_vq_fwd<12, 8>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st)
+                        : launch_vq_fwd<12, 4>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st); break;
+    case 16: rc = rows8 ? launch_vq_fwd<16, 8>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st)
+                        : launch_vq_fwd<16, 4>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st); break;
     case 20: case 24: case 28: case 32:
       // pad to 32 is not possible without changing DP; dispatch exact sizes used in practice
       if (DP == 32) { rc = launch_vq_fwd<32, 2>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st); break; }
