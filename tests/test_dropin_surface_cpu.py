@@ -77,14 +77,21 @@ else:
     sys.modules["lpips"] = types.ModuleType("lpips")
     m = types.ModuleType("vector_quantize_pytorch"); m.FSQ = object; sys.modules["vector_quantize_pytorch"] = m
 import torch
-import transformer, train_vit, train_titok
+import transformer, train_vit, train_titok, train_videogpt, train_vit_vqgan
 out = {}
 transformer.transformer_configs.setdefault("Ti", lambda **kw: transformer.TransformerConfig(12, 3, 192, **kw))
 vit = train_vit.ViTClassifier(train_vit.ViTConfig(32, 3, 4, "Ti", 1, 0.0), num_classes=10)
 out["vit"] = {k: list(v.shape) for k, v in vit.state_dict().items()}
 titok = train_titok.TiTok(train_titok.TiTokConfig(256, 16, 32, 4096, 12, "S"))
 out["titok"] = {k: list(v.shape) for k, v in titok.state_dict().items()}
-out["classes"] = [type(titok.enc.vit).__module__, type(titok.quant).__module__, type(vit.vit.transformer).__module__]
+transformer.transformer_configs.setdefault("XS", lambda **kw: transformer.TransformerConfig(2, 1, 64, **kw))
+gpt = train_videogpt.VideoGPT(train_videogpt.VideoGPTConfig(8, 32, "XS", 4, 0.0))
+out["videogpt"] = {k: list(v.shape) for k, v in gpt.state_dict().items()}
+vqgan = train_vit_vqgan.ViTVQGAN(train_vit_vqgan.ViTVQGANConfig(32, 4, 64, 12, "XS"))
+out["vqgan"] = {k: list(v.shape) for k, v in vqgan.state_dict().items()}
+out["classes"] = [type(titok.enc.vit).__module__, type(titok.quant).__module__, type(vit.vit.transformer).__module__,
+                  type(titok.enc).__module__, type(titok.dec).__module__, type(gpt).__module__, type(vqgan.encoder).__module__,
+                  type(vqgan.decoder).__module__]
 print("RESULT" + json.dumps(out))
 """
 
@@ -99,5 +106,7 @@ def test_launcher_swaps_classes_and_keeps_state_dict_contract():
     ref, ours = run("reference"), run("dropin")
     assert ours["vit"] == ref["vit"], "ViTClassifier state_dict keys/shapes must equal the reference's"
     assert ours["titok"] == ref["titok"], "TiTok (train_titok.py) state_dict keys/shapes must equal the reference's"
+    assert ours["videogpt"] == ref["videogpt"], "VideoGPT (train_videogpt.py) state_dict keys/shapes must equal the reference's"
+    assert ours["vqgan"] == ref["vqgan"], "ViTVQGAN (train_vit_vqgan.py) state_dict keys/shapes must equal the reference's"
     assert all(c.startswith("b200vit") for c in ours["classes"]), ours["classes"]
     assert not any(c.startswith("b200vit") for c in ref["classes"])
