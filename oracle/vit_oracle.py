@@ -326,6 +326,118 @@ def vit_classifier_loss_and_grads(x, labels, P, n_heads):
 
 
 # ------------------------------------------------------------------------------------------------
+# Steps either side of the stack: token-range Linear (classifier head train_vit.py:53, TiTokEncoder.proj
+# train_titok.py:41-42, VideoGPT.proj train_videogpt.py:52), de-patchify tail (train_titok.py:67,71-74), token + positional
+# embedding (train_videogpt.py:45-50), VideoGPT forward / greedy generate (train_videogpt.py:44-65)
+# ------------------------------------------------------------------------------------------------
+def token_linear_fwd(x, w, b, t0, cnt):
+    """y[B, cnt, C] = x[:, t0:t0+cnt] @ w^T + b."""
+    rows = x[:, t0:t0 + cnt]
+    return rows @ w.T + b, (rows, w, x.shape, t0, cnt)
+
+
+def token_linear_bwd(dy, cache):
+    rows, w, xshape, t0, cnt = cache
+    d = rows.shape[-1]
+    dw = dy.reshape(-1, dy.shape[-1]).T @ rows.reshape(-1, d)
+    db = dy.reshape(-1, dy.shape[-1]).sum(axis=0)
+    dx = np.zeros(xshape, dtype=dy.dtype)
+    dx[:, t0:t0 + cnt] = dy @ w
+    return dx, dw, db
+
+
+def depatchify_fwd(tokens, conv_w, conv_b, Ht, Wt, p):
+    """tokens[:, :Ht*Wt] -> 'b (h w) c -> b c h w' -> Conv2d(d, C*p*p, 1) -> 'b (p1 p2 c) h w -> b c (h p1) (w p2)'."""
+    B, N, d = tokens.shape
+    P = Ht * Wt
+    Cpp = conv_w.shape[0]
+    C = Cpp // (p * p)
+    rows = tokens[:, :P]
+    y = rows @ conv_w.reshape(Cpp, d).T + conv_b                       # [B, P, (p1 p2 c)]
+    img = y.reshape(B, Ht, Wt, p, p, C).transpose(0, 5, 1, 3, 2, 4).reshape(B, C, Ht * p, Wt * p)
+    return img, (rows, conv_w, tokens.shape, Ht, Wt, p, C)
+
+
+def depatchify_bwd(dimg, cache):
+    rows, conv_w, tshape, Ht, Wt, p, C = cache
+    B, d = rows.shape[0], rows.shape[-1]
+    dy = dimg.reshape(B, C, Ht, p, Wt, p).transpose(0, 2, 4, 3, 5, 1).reshape(B, Ht * Wt, p * p * C)   # (p1 p2 c) order
+    dw = (dy.reshape(-1, dy.shape[-1]).T @ rows.reshape(-1, d)).reshape(conv_w.shape)
+    db = dy.reshape(-1, dy.shape[-1]).sum(axis=0)
+    dtok = np.zeros(tshape, dtype=dimg.dtype)
+    dtok[:, :Ht * Wt] = dy @ conv_w.reshape(-1, d)
+    return dtok, dw, db
+
+
+def embed_fwd(idx, tok_embed, pos_embed, pos0=0):
+    S = idx.shape[1]
+    return tok_embed[idx] + pos_embed[pos0:pos0 + S][None], (idx, tok_embed.shape, pos_embed.shape, pos0)
+
+
+def embed_bwd(dy, cache):
+    idx, tshape, pshape, pos0 = cache
+    dtok = np.zeros(tshape, dtype=dy.dtype)
+    np.add.at(dtok, idx.reshape(-1), dy.reshape(-1, dy.shape[-1]))
+    dpos = np.zeros(pshape, dtype=dy.dtype)
+    dpos[pos0:pos0 + dy.shape[1]] = dy.sum(axis=0)
+    return dtok, dpos
+
+
+def titok_encoder_fwd(x, P, n_heads, latent_tokens):
+    """train_titok.TiTokEncoder.forward (train_titok.py:40-43); P = vit params + proj_w / proj_b."""
+    tokens, _ = vit_fwd(x, P, n_heads)
+    lat, c = token_linear_fwd(tokens, P["proj_w"], P["proj_b"], 0, latent_tokens)
+    return lat, tokens, c
+
+
+def titok_decoder_fwd(z, P, n_heads, patch_dim, p):
+    """train_titok.TiTokDecoder.forward (train_titok.py:69-76); P = vit params + quant_proj_w/b + embd_proj_w/b."""
+    h = z @ P["quant_proj_w"].T + P["quant_proj_b"]                    # [B, L, d]
+    zimg = h.transpose(0, 2, 1)[..., None]                             # 'b h c -> b c h 1'
+    tokens, _ = vit_fwd(zimg, P, n_heads)
+    img, c = depatchify_fwd(tokens, P["embd_proj_w"], P["embd_proj_b"], patch_dim, patch_dim, p)
+    return img, tokens, c
+
+
+def videogpt_fwd(x, P, n_heads, codebook_size):
+    """train_videogpt.VideoGPT.forward (train_videogpt.py:44-55): x [B, T, N] int tokens -> (logits, loss, caches)."""
+    B = x.shape[0]
+    y = x.reshape(B, -1)
+    sos = np.full((B, 1), codebook_size, dtype=y.dtype)
+    inp = np.concatenate([sos, y[:, :-1]], axis=1)
+    h0, c_emb = embed_fwd(inp, P["tok_embed"], P["pos_embed"])
+    h, c_tr = transformer_fwd(h0, P["layers"], n_heads, True)
+    logits, c_proj = token_linear_fwd(h, P["proj_w"], P["proj_b"], 0, h.shape[1])
+    loss, c_ce = cross_entropy_fwd(logits.reshape(-1, logits.shape[-1]), y.reshape(-1))
+    return logits, loss, (c_emb, c_tr, c_proj, c_ce, logits.shape)
+
+
+def videogpt_bwd(caches):
+    c_emb, c_tr, c_proj, c_ce, lshape = caches
+    dlogits = cross_entropy_bwd(c_ce).reshape(lshape)
+    dh, dpw, dpb = token_linear_bwd(dlogits, c_proj)
+    dh0, layer_grads = transformer_bwd(dh, c_tr)
+    dtok, dpos = embed_bwd(dh0, c_emb)
+    return {"tok_embed": dtok, "pos_embed": dpos, "proj_w": dpw, "proj_b": dpb, "layers": layer_grads}
+
+
+def videogpt_generate(tokens, n, P, n_heads, codebook_size):
+    """train_videogpt.VideoGPT.generate (train_videogpt.py:56-65): the whole stack is re-run for every new token.
+    Returns (tokens [B, T0 + n], top-2 logit margins [B, n])."""
+    margins = []
+    for _ in range(n):
+        B = tokens.shape[0]
+        sos = np.full((B, 1), codebook_size, dtype=tokens.dtype)
+        h0, _ = embed_fwd(np.concatenate([sos, tokens], axis=1), P["tok_embed"], P["pos_embed"])
+        h, _ = transformer_fwd(h0, P["layers"], n_heads, True)
+        lg = h[:, -1] @ P["proj_w"].T + P["proj_b"]
+        top2 = np.sort(lg, axis=-1)[:, -2:]
+        margins.append(top2[:, 1] - top2[:, 0])
+        tokens = np.concatenate([tokens, lg.argmax(axis=-1)[:, None].astype(tokens.dtype)], axis=1)
+    return tokens, np.stack(margins, axis=1)
+
+
+# ------------------------------------------------------------------------------------------------
 # VQ lookups
 # ------------------------------------------------------------------------------------------------
 def _normalize(x, eps=1e-12):

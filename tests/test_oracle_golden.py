@@ -220,3 +220,104 @@ def test_cross_entropy_oracle(golden_dir, tag):
     loss, cache = O.cross_entropy_fwd(g[f"{tag}_x"], g[f"{tag}_y"])
     np.testing.assert_allclose(loss, g[f"{tag}_loss"], rtol=1e-5)
     np.testing.assert_allclose(O.cross_entropy_bwd(cache), g[f"{tag}_dx"], rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ §8f rows
+def _np_weights(shapes_in_state_dict_order, seed, scale):
+    """tests/golden/make_golden.py:det_weights: numpy Generator values in state_dict order (masks excluded by the caller)."""
+    rng = np.random.default_rng(seed)
+    return {k: rng.standard_normal(s).astype(np.float32) * scale for k, s in shapes_in_state_dict_order}
+
+
+def _vit_shapes(prefix, d, L, C, p, n_pos, extra):
+    out = [(prefix + "patch_proj.weight", (d, C, p, p)), (prefix + "patch_proj.bias", (d,)),
+           (prefix + "pos_emb.weight", (n_pos, d)), (prefix + "extra_emb.weight", (extra, d))]
+    for i in range(L):
+        k = f"{prefix}transformer.layers.{i}."
+        out += [(k + "multi_attn.qkv.weight", (3 * d, d)), (k + "multi_attn.qkv.bias", (3 * d,)),
+                (k + "mlp.0.weight", (4 * d, d)), (k + "mlp.0.bias", (4 * d,)),
+                (k + "mlp.2.weight", (d, 4 * d)), (k + "mlp.2.bias", (d,))]
+    return out
+
+
+def _vit_P(w, prefix, L):
+    return {"conv_w": w[prefix + "patch_proj.weight"], "conv_b": w[prefix + "patch_proj.bias"],
+            "pos_emb": w[prefix + "pos_emb.weight"], "extra_emb": w[prefix + "extra_emb.weight"],
+            "layers": [{"qkv_w": w[f"{prefix}transformer.layers.{i}.multi_attn.qkv.weight"],
+                        "qkv_b": w[f"{prefix}transformer.layers.{i}.multi_attn.qkv.bias"],
+                        "fc1_w": w[f"{prefix}transformer.layers.{i}.mlp.0.weight"], "fc1_b": w[f"{prefix}transformer.layers.{i}.mlp.0.bias"],
+                        "fc2_w": w[f"{prefix}transformer.layers.{i}.mlp.2.weight"], "fc2_b": w[f"{prefix}transformer.layers.{i}.mlp.2.bias"]}
+                       for i in range(L)]}
+
+
+def test_titok_encoder_decoder_oracle(golden_dir):
+    """oracle titok_encoder_fwd / titok_decoder_fwd / token_linear_bwd / depatchify_bwd against the reference's
+    train_titok.TiTokEncoder / TiTokDecoder (tests/golden/titok.npz, make_golden.py titok)."""
+    g = _load(golden_dir, "titok.npz")
+    img_size, p, latent, K, D = (int(v) for v in g["cfg"])
+    d, L, P_ = 64, 2, (img_size // p) ** 2
+    shapes = _vit_shapes("vit.", d, L, 3, p, P_, latent) + [("proj.weight", (D, d)), ("proj.bias", (D,))]
+    assert [k for k, _ in shapes] == [str(k) for k in g["enc_keys"]]
+    w = _np_weights(shapes, 41, 0.05)
+    P = _vit_P(w, "vit.", L)
+    P["proj_w"], P["proj_b"] = w["proj.weight"], w["proj.bias"]
+    lat, tokens, c = O.titok_encoder_fwd(g["enc_x"], P, 1, latent)
+    _close(lat, g["enc_lat"])
+    _, dw, db = O.token_linear_bwd(g["enc_dlat"], c)
+    _close(dw, g["enc_g_proj.weight"], rtol=5e-4, atol=5e-5)
+    _close(db, g["enc_g_proj.bias"], rtol=5e-4, atol=5e-5)
+    # decoder: the "image" is [B, d, latent, 1], patch 1, n_patches mask tokens prepended
+    shapes = _vit_shapes("vit.", d, L, d, 1, latent, P_) + [("quant_proj.weight", (d, D)), ("quant_proj.bias", (d,)),
+                                                             ("embd_proj.weight", (3 * p * p, d, 1, 1)), ("embd_proj.bias", (3 * p * p,))]
+    assert [k for k, _ in shapes] == [str(k) for k in g["dec_keys"]]
+    w = _np_weights(shapes, 42, 0.05)
+    P = _vit_P(w, "vit.", L)
+    P.update(quant_proj_w=w["quant_proj.weight"], quant_proj_b=w["quant_proj.bias"],
+             embd_proj_w=w["embd_proj.weight"], embd_proj_b=w["embd_proj.bias"])
+    img, tokens, c = O.titok_decoder_fwd(g["dec_z"], P, 1, img_size // p, p)
+    _close(img, g["dec_img"])
+    _, dw, db = O.depatchify_bwd(g["dec_dimg"], c)
+    _close(dw, g["dec_g_embd_proj.weight"], rtol=5e-4, atol=5e-5)
+    _close(db, g["dec_g_embd_proj.bias"], rtol=5e-4, atol=5e-5)
+
+
+def _videogpt_P(seed, scale, keys):
+    d, L, V, S = 64, 2, 32, 32
+    shapes = [("tok_embed.weight", (V + 1, d)), ("pos_embed.weight", (S, d))]
+    for i in range(L):
+        k = f"transformer.layers.{i}."
+        shapes += [(k + "multi_attn.mask", (S, S)), (k + "multi_attn.qkv.weight", (3 * d, d)), (k + "multi_attn.qkv.bias", (3 * d,)),
+                   (k + "mlp.0.weight", (4 * d, d)), (k + "mlp.0.bias", (4 * d,)), (k + "mlp.2.weight", (d, 4 * d)), (k + "mlp.2.bias", (d,))]
+    shapes += [("proj.weight", (V, d)), ("proj.bias", (V,))]
+    assert [k for k, _ in shapes] == [str(k) for k in keys]
+    w = _np_weights([(k, s) for k, s in shapes if not k.endswith("mask")], seed, scale)   # det_weights skips the masks
+    P = {"tok_embed": w["tok_embed.weight"], "pos_embed": w["pos_embed.weight"], "proj_w": w["proj.weight"], "proj_b": w["proj.bias"],
+         "layers": [{"qkv_w": w[f"transformer.layers.{i}.multi_attn.qkv.weight"], "qkv_b": w[f"transformer.layers.{i}.multi_attn.qkv.bias"],
+                     "fc1_w": w[f"transformer.layers.{i}.mlp.0.weight"], "fc1_b": w[f"transformer.layers.{i}.mlp.0.bias"],
+                     "fc2_w": w[f"transformer.layers.{i}.mlp.2.weight"], "fc2_b": w[f"transformer.layers.{i}.mlp.2.bias"]} for i in range(L)]}
+    return P
+
+
+def test_videogpt_oracle(golden_dir):
+    """oracle videogpt_fwd / videogpt_bwd / videogpt_generate against train_videogpt.VideoGPT (tests/golden/videogpt.npz)."""
+    g = _load(golden_dir, "videogpt.npz")
+    P = _videogpt_P(51, 0.1, g["keys"])
+    logits, loss, caches = O.videogpt_fwd(g["x"], P, 1, 32)
+    _close(logits, g["logits"], rtol=1e-3, atol=1e-4)
+    _close(loss, g["loss"], rtol=1e-4)
+    grads = O.videogpt_bwd(caches)
+    for name, key in (("tok_embed", "tok_embed.weight"), ("pos_embed", "pos_embed.weight"), ("proj_w", "proj.weight"), ("proj_b", "proj.bias")):
+        _close(grads[name], g[f"g_{key}"], rtol=2e-3, atol=2e-5)
+    for i in range(2):
+        ref = float(g[f"gn_transformer.layers.{i}.mlp.0.weight"])
+        assert abs(np.linalg.norm(grads["layers"][i]["fc1_w"].astype(np.float64)) - ref) < 2e-3 * ref
+    # greedy generation: identical tokens up to the first near-tie of the reference (fp32 both sides: margin 1e-3 is ample)
+    P = _videogpt_P(53, 0.3, g["keys"])
+    toks, margins = O.videogpt_generate(g["prompt"], 12, P, 1, 32)
+    ref, ref_m = g["generated"], g["margins"]
+    for b in range(ref.shape[0]):
+        for j in range(12):
+            if ref_m[b, j] < 1e-2:
+                break
+            assert toks[b, 5 + j] == ref[b, 5 + j], (b, j)
+            assert abs(margins[b, j] - ref_m[b, j]) < 2e-2 * max(1.0, ref_m[b, j])
