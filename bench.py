@@ -195,9 +195,9 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_model(torch, M, device):
+def build_model(torch, M, device, dropout=0.0):
     torch.manual_seed(0)
-    cfg = M.ViTConfig(IMAGE, 3, PATCH, "B", 1, 0.0)
+    cfg = M.ViTConfig(IMAGE, 3, PATCH, "B", 1, dropout)
     model = M.ViTClassifier(cfg, num_classes=CLASSES).to(device)
     return model
 
@@ -222,7 +222,7 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=device)
 
     B = args.batch
-    model = build_model(torch, M, device)
+    model = build_model(torch, M, device, args.dropout)
     wrapped = b200_ddp.DataParallel(model, bucket_mb=args.bucket_mb) if world > 1 else model
     from b200vit import optim as b200_optim
     if args.optimizer == "torch-fused":
@@ -343,7 +343,7 @@ def run_gpu_arm(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "ViT-B/16 224px ImageNet-shape train step (fwd + CE + bwd + AdamW), configs[1]",
-                   "per_gpu_batch": B, "global_batch": B * world, "seq_len": NTOK, "parallelism": f"dp{world}",
+                   "per_gpu_batch": B, "global_batch": B * world, "seq_len": NTOK, "parallelism": f"dp{world}", "dropout": args.dropout,
                    "optimizer": "torch.optim.AdamW(fused=True)" if args.optimizer == "torch-fused" else "b200vit.optim.AdamW (fused multi-tensor + bf16 operand refresh)", "l2": "per-step working set >> 126 MB L2 (no flush needed)",
                    "train_gflop_per_image": train_flops_per_image() / 1e9},
         "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -385,6 +385,9 @@ def main():
     ap.add_argument("--impl", type=str, default="b200vit", choices=["b200vit", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU-baseline sample (one step is ~4 s on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="ViTConfig.dropout (SDPA dropout_p + nn.Dropout after mlp[2]); train_vit.py's own default is 0.15. "
+                         "The headline number is measured at 0.0 (BASELINE configs[1]); other values are for throughput only")
     ap.add_argument("--optimizer", type=str, default="b200vit", choices=["b200vit", "torch-fused"],
                     help="AdamW implementation inside the step (default: the fused kernel of this library)")
     args = ap.parse_args()
