@@ -224,6 +224,7 @@ def _attn_case(ops, B, N, H, causal, seed):
 
 @pytest.mark.parametrize("B,N,H,causal", [(2, 16, 1, False), (2, 65, 3, False), (1, 128, 2, False), (3, 197, 2, False),
                                           (2, 257, 1, False), (2, 288, 2, False), (1, 320, 1, False),
+                                          (1, 273, 1, False), (2, 400, 1, False), (1, 300, 2, True), (1, 417, 1, True),
                                           (2, 16, 1, True), (1, 200, 2, True), (1, 1024, 1, True)])
 def test_flash_attention(ops, B, N, H, causal):
     _attn_case(ops, B, N, H, causal, seed=N + H)

@@ -769,7 +769,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     }
   } else if (warp == 5) {
     const bool elected = elect_one();   // warp-uniform control flow, one elected lane issues
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, AT_BK, false, false);   // S, dP: K-major x K-major
+    // ragged last key block (N = 288: 32 of 128 keys): S / dP are only computed for the 32-key chunks that hold a valid
+    // key and dQ only contracts over the valid keys; ragged last query tile: dV / dK only contract over the valid
+    // query rows.  Columns / rows beyond are never read (dK / dV rows of invalid keys are not written out).
+    const int nkeys = min(AT_BK, p.N - k0);
+    const int ncols = ((nkeys + 31) >> 5) << 5;
+    const int ksteps_dq = (nkeys + 15) >> 4;
+    const uint32_t idesc_s = umma_idesc_bf16(128, ncols, false, false);       // S, dP: K-major x K-major
     constexpr uint32_t idesc_t = umma_idesc_bf16(128, AT_HD, true, true);     // dV, dK: MN-major x MN-major
     constexpr uint32_t idesc_q = umma_idesc_bf16(128, AT_HD, false, true);    // dQ: K-major x MN-major
     const uint32_t sK = smem_u32(smem + BwdSmem::K), sV = smem_u32(smem + BwdSmem::V);
@@ -793,9 +799,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       mbar_wait(pds_ready, it & 1, 52);
       tc_fence_after();
       // dV[key, d] += P^T dO ; dK[key, d] += dS^T Q   (contraction over the 128 query rows)
+      const int qsteps = (min(AT_BQ, p.N - (i0 + it) * AT_BQ) + 15) >> 4;   // 16-row slabs holding a valid query
       if (elected) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
+#pragma unroll 2
+        for (int k = 0; k < qsteps; ++k) {
           umma_bf16(tmem_dV, desc_mnmajor(sP, k, 16384), desc_mnmajor(sDO, k, 8192), idesc_t, (it > 0 || k > 0) ? 1u : 0u);
           umma_bf16(tmem_dK, desc_mnmajor(sDS, k, 16384), desc_mnmajor(sQ, k, 8192), idesc_t, (it > 0 || k > 0) ? 1u : 0u);
         }
@@ -804,8 +811,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       if (it > 0) { mbar_wait(dq_free, (it - 1) & 1, 53); tc_fence_after(); }
       // dQ[q, d] = dS K   (contraction over the 128 keys)
       if (elected) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
+#pragma unroll 2
+        for (int k = 0; k < ksteps_dq; ++k)
           umma_bf16(tmem_dQ, desc_kmajor(sDS + (k >> 2) * AT_TILE_BYTES, k & 3), desc_mnmajor(sK, k, 8192), idesc_q, k > 0);
         umma_commit(dq_full);
         umma_commit(&q_empty[st]);
@@ -821,6 +828,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int quarter = warp & 3;                 // TMEM lane quarter == warp % 4
     const int r = quarter * 32 + lane;            // query row within the tile
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int nch = (min(AT_BK, p.N - k0) + 31) >> 5;   // 32-key chunks holding at least one valid key
     for (int it = 0; it < ntiles; ++it) {
       const int q = (i0 + it) * AT_BQ + r;
       const bool qv = q < p.N;
@@ -832,7 +840,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       mbar_wait(sdp_full, it & 1, 60);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 2 * grp; c < 2 * grp + 2; ++c) {
+      for (int c = 2 * grp; c < min(2 * grp + 2, nch); ++c) {
         uint32_t s[32], dp[32];
         tmem_ld32(tmem_S + lane_off + c * 32, s);
         tmem_ld32(tmem_dP + lane_off + c * 32, dp);
