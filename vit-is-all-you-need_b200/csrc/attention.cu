@@ -47,6 +47,7 @@ struct AttnParams {
   // dropout on the attention probabilities (dropout_p of SDPA, transformer.py:28); drop_thr == 0: none
   uint32_t drop_seed, drop_thr;
   float drop_r;                // 1 / (1 - p)
+  int dbg_skip_dq;             // bring-up knob 8: the streaming backward skips its dQ atomics (timing experiments only)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -881,7 +882,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         uint32_t v[32];
         tmem_ld32(tmem_dQ + lane_off + c * 32, v);
         tmem_ld_wait();
-        if (qv) {
+        if (qv && !p.dbg_skip_dq) {
           float* dst = p.dq_acc + ((long long)b * p.sb + q * p.sn) * p.d + hh * AT_HD + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
@@ -1684,6 +1685,7 @@ int b200vit_flash_attn_bwd_dropout(const void* qkv, const void* o, const void* d
   p.o_in = (const __nv_bfloat16*)o; p.do_in = (const __nv_bfloat16*)d_o;
   p.dq_acc = (float*)workspace; p.dqkv = (__nv_bfloat16*)dqkv;
   p.drop_seed = seed; p.drop_thr = dropout_p > 0.f ? drop_threshold(dropout_p) : 0u; p.drop_r = 1.0f / (1.0f - dropout_p);
+  p.dbg_skip_dq = g_debug[8];
   if (!causal && N <= 208 && g_debug[7] == 0) {
     // short sequences, transposed formulation: persistent, whole head resident, P^T kept in TMEM
     const int ncols = ((N + 15) / 16) * 16, nt = (N + 127) / 128;
