@@ -43,6 +43,62 @@ for it in range(2):
         assert err < 2e-2, (n, err)
     if rank == 0:
         print(f"iteration {it}: max rel-L2 gradient difference over {len(list(ref.parameters()))} parameters = {worst:.3e}")
+
+
+# ---- the other drop-in model families through the same wrapper (their extra parameters take the hook path) ----------------
+class _TiTokCfg:   # train_titok.TiTokConfig (train_titok.py:18-32)
+    def __init__(self, image_size, patch_size, latent_tokens, codebook_size, latent_dim, transformer):
+        self.image_size, self.patch_size, self.latent_tokens = image_size, patch_size, latent_tokens
+        self.codebook_size, self.latent_dim, self.transformer = codebook_size, latent_dim, transformer
+        self.patch_dim = image_size // patch_size
+        self.n_patches = self.patch_dim ** 2
+        self.enc_vit_config = M.ViTConfig(image_size, 3, patch_size, transformer, latent_tokens, 0.0)
+        self.n_embd = self.enc_vit_config.trans_config.n_embd
+        self.dec_vit_config = M.ViTConfig(latent_tokens, self.n_embd, 1, transformer, self.n_patches, 0.0)
+        self.dec_vit_config.n_patches = latent_tokens
+
+
+class _GPTCfg:     # train_videogpt.VideoGPTConfig (train_videogpt.py:18-28)
+    def __init__(self):
+        self.frame_size, self.codebook_size, self.transformer, self.max_frames, self.dropout = 16, 64, "XS2", 4, 0.0
+        self.max_tokens = 64
+        self.trans_config = M.transformer_configs["XS2"](block_size=64, dropout=0.0, causal=True)
+        self.n_embd = self.trans_config.n_embd
+
+
+M.transformer_configs["XS2"] = lambda **kw: M.TransformerConfig(n_layers=2, n_heads=2, n_embd=128, **kw)
+
+
+def check(name, make, batch, loss_of, tol=3e-2):
+    torch.manual_seed(0)
+    ref, par = make().to(dev), make().to(dev)
+    par.load_state_dict(ref.state_dict())
+    wrapped = ddp.DataParallel(par, bucket_mb=1.0)
+    xs = batch()
+    n = xs.shape[0] // world
+    ref.zero_grad(set_to_none=True); par.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss_of(ref, xs).backward()
+        loss_of(wrapped, xs[rank * n:(rank + 1) * n]).backward()
+    torch.cuda.synchronize()
+    worst, wn = 0.0, None
+    for (k, a), b in zip(ref.named_parameters(), par.parameters()):
+        assert b.grad is not None, k
+        err = ((a.grad - b.grad).norm() / (a.grad.norm() + 1e-12)).item()
+        if err > worst:
+            worst, wn = err, k
+    if rank == 0:
+        print(f"{name}: max rel-L2 gradient difference = {worst:.3e} ({wn})")
+    assert worst < tol, (name, wn, worst)
+
+
+gg = torch.Generator(device="cpu").manual_seed(2)
+check("TiTok (enc + VQ + dec)", lambda: M.TiTok(_TiTokCfg(32, 4, 8, 64, 12, "XS2")),
+      lambda: torch.rand(4 * world, 3, 32, 32, generator=gg).to(dev),
+      lambda m, xb: (lambda out: torch.nn.functional.mse_loss(out[0], xb) + out[2])(m(xb)))
+check("VideoGPT", lambda: M.VideoGPT(_GPTCfg()),
+      lambda: torch.randint(0, 64, (2 * world, 4, 16), generator=gg).to(dev),
+      lambda m, xb: m(xb)[1])
 dist.destroy_process_group()
 if rank == 0:
     print("DDP gradient check OK")
