@@ -170,12 +170,16 @@ int b200vit_embed_fwd(const long long* idx, const float* tok_embed, const float*
 int b200vit_embed_bwd(const long long* idx, const float* dy, float* dtok, float* dpos, int B, int S, int d, int vocab,
                       void* stream);
 
-/* incremental decode attention for VideoGPT.generate (train_videogpt.py:56-65): kv_cache[B, Nmax, 3, H, 64] bf16 in the
- * layout of the fused QKV projection; kv_append writes the new token's fused q|k|v row at position *pos_dev, then
- * out_bf16[B, H*64] = softmax(q_pos . K[0..pos]^T / 8) V[0..pos].  The position is read from DEVICE memory so that one
- * captured CUDA graph serves every step of a generation; advance_counter bumps it at the end of the step.      */
-int b200vit_attn_decode(const void* kv_cache, void* out_bf16, int B, int Nmax, int H, const int* pos_dev, void* stream);
-int b200vit_kv_append(const void* rows_bf16, void* kv_cache, int B, int Nmax, int row_elems, const int* pos_dev, void* stream);
+/* incremental decode attention for VideoGPT.generate (train_videogpt.py:56-65).  kv_cache[2][B][H][Nmax][64] bf16: K planes
+ * then V planes, one head's rows contiguous (the fused-QKV layout made every key row an isolated 128-byte piece: ~2 TB/s).
+ * kv_fill copies the prompt's fused QKV projection qkv[B, S, 3, H, 64] into rows 0..S; kv_append writes the K / V of the
+ * new token (slots 1, 2 of its fused row qkv_rows[B, 3*H*64]) at position *pos_dev; attn_decode:
+ * out_bf16[B, H*64] = softmax(q . K[0..pos]^T / 8) V[0..pos] with q = slot 0 of qkv_rows.  The position is read from DEVICE
+ * memory so that one captured CUDA graph serves every step of a generation; advance_counter bumps it.         */
+int b200vit_attn_decode(const void* qkv_rows, const void* kv_cache, void* out_bf16, int B, int Nmax, int H, const int* pos_dev,
+                        void* stream);
+int b200vit_kv_append(const void* qkv_rows, void* kv_cache, int B, int Nmax, int H, const int* pos_dev, void* stream);
+int b200vit_kv_fill(const void* qkv, void* kv_cache, int B, int S, int Nmax, int H, void* stream);
 int b200vit_advance_counter(int* counter, int by, void* stream);
 
 /* ---- fused multi-tensor AdamW + bf16 operand refresh (torch.optim.AdamW at train_vit.py:82,105, ------------

@@ -488,20 +488,24 @@ def test_depatchify_gemm_epilogue(ops, B, Ht, Wt, p, C, d):
 
 @pytest.mark.parametrize("B,H,Nmax,pos", [(3, 2, 40, 0), (2, 12, 64, 17), (4, 1, 300, 299), (1, 3, 1024, 1023)])
 def test_attn_decode_against_oracle(ops, B, H, Nmax, pos):
-    # one query (the row at `pos`) against the cached keys / values 0..pos: oracle sdpa_fwd on the same bf16 values
+    # one query (the new token) against the cached keys / values 0..pos: oracle sdpa_fwd on the same bf16 values.
+    # The cache is filled through kv_fill (prompt rows 0..pos-1) + kv_append (the new token's row), as generate() does.
     rng = np.random.default_rng(B + H + pos)
-    cache = bf16_round(rng.standard_normal((B, Nmax, 3, H, 64)).astype(np.float32))
+    qkv = bf16_round(rng.standard_normal((B, pos + 1, 3, H, 64)).astype(np.float32))      # fused QKV rows of positions 0..pos
+    cache = ops.kv_cache_alloc(B, H, Nmax, DEV)
+    cache.fill_(float("nan"))                                                             # unused rows must never be read
     pos_dev = torch.tensor([pos], device=DEV, dtype=torch.int32)
-    cd = to_dev(cache, torch.bfloat16)
-    # the new token's fused q|k|v row goes in through kv_append (cache row `pos` is garbage before)
-    row = cd[:, pos].reshape(B, -1).clone()
-    cd[:, pos] = 0
-    ops.kv_append(row, cd, pos_dev)
-    o = ops.attn_decode(cd, pos_dev)
+    if pos > 0:
+        ops.kv_fill(to_dev(np.ascontiguousarray(qkv[:, :pos]).reshape(B * pos, -1), torch.bfloat16), cache, B, pos)
+    new_rows = to_dev(np.ascontiguousarray(qkv[:, pos]).reshape(B, -1), torch.bfloat16)
+    ops.kv_append(new_rows, cache, pos_dev)
+    o = ops.attn_decode(new_rows, cache, pos_dev)
     ops.advance_counter(pos_dev, 1)
     assert int(pos_dev.item()) == pos + 1
-    q = cache[:, pos:pos + 1, 0].transpose(0, 2, 1, 3).astype(np.float64)           # [B, H, 1, 64]
-    k = cache[:, :pos + 1, 1].transpose(0, 2, 1, 3).astype(np.float64)
-    v = cache[:, :pos + 1, 2].transpose(0, 2, 1, 3).astype(np.float64)
-    ref, _ = O.sdpa_fwd(q, k, v, causal=False)                                      # [B, H, 1, 64]
+    q = qkv[:, pos:pos + 1, 0].transpose(0, 2, 1, 3).astype(np.float64)                   # [B, H, 1, 64]
+    k = qkv[:, :, 1].transpose(0, 2, 1, 3).astype(np.float64)
+    v = qkv[:, :, 2].transpose(0, 2, 1, 3).astype(np.float64)
+    ref, _ = O.sdpa_fwd(q, k, v, causal=False)                                            # [B, H, 1, 64]
     assert_close_bf16(o, ref[:, :, 0].reshape(B, H * 64), "decode attention", rel=5e-3)
+    kc = cache[0, :, :, :pos + 1].float().cpu().numpy()                                   # [B, H, pos+1, 64]
+    assert np.array_equal(kc, qkv[:, :, 1].transpose(0, 2, 1, 3))

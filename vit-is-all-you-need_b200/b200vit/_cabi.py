@@ -75,8 +75,9 @@ _SIGNATURES = {
     "b200vit_cross_entropy_bwd": (_I, [_P, _I, _L, _P, _P, _P, _P, _P, _L, _I, _I, _L, _P]),
     "b200vit_embed_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
     "b200vit_embed_bwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "b200vit_attn_decode": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "b200vit_attn_decode": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "b200vit_kv_append": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "b200vit_kv_fill": (_I, [_P, _P, _I, _I, _I, _I, _P]),
     "b200vit_advance_counter": (_I, [_P, _I, _P]),
     "b200vit_adamw_chunk_elems": (_I, []),
     "b200vit_adamw_step": (_I, [_P, _P, _I, _D, _D, _D, _D, _D, _L, _P, _P, _P, _P]),

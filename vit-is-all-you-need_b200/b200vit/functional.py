@@ -461,15 +461,15 @@ class DepatchifyFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
 def stack_prefill(x, layers, n_heads, n_max):
-    """x [B, S, d] fp32 through the causal stack; returns (h [B, S, d] fp32, caches: one [B, n_max, 3, H, 64] bf16 per layer)."""
+    """x [B, S, d] fp32 through the causal stack; returns (h [B, S, d] fp32, caches: one [2, B, H, n_max, 64] bf16 per layer)."""
     B, S, d = x.shape
     h = _as_rows_f32(x).view(B * S, d)
     caches = []
     for P in layers:
         h, saved = layer_forward(h, P, B, S, n_heads, True, True)
         qkv = saved[2]                                             # [B*S, 3d] bf16 == [B, S, 3, H, 64]
-        cache = torch.empty(B, n_max, 3, n_heads, 64, device=x.device, dtype=BF16)
-        cache[:, :S].copy_(qkv.view(B, S, 3, n_heads, 64))
+        cache = ops.kv_cache_alloc(B, n_heads, n_max, x.device)
+        ops.kv_fill(qkv, cache, B, S)
         caches.append(cache)
     return h.view(B, S, d), caches
 
@@ -484,7 +484,7 @@ def stack_decode_step(x, layers, caches, pos_dev):
         a, _, _, _, _ = ops.layernorm_fwd(h)
         qkv = ops.gemm_bias(a, bf16_of(P.qkv_w), _f32c(P.qkv_b))   # [B, 3d]
         ops.kv_append(qkv, cache, pos_dev)
-        o = ops.attn_decode(cache, pos_dev)
+        o = ops.attn_decode(qkv, cache, pos_dev)
         b, _, _, _, x1 = ops.layernorm_fwd(h, add=o, want_x_out=True)
         g, _ = ops.gemm_bias_gelu(b, bf16_of(P.fc1_w), _f32c(P.fc1_b))
         h = ops.gemm_bias_residual(g, bf16_of(P.fc2_w), _f32c(P.fc2_b), x1)

@@ -275,26 +275,36 @@ def cast_bf16(t, out=None):
 
 
 # ---------------------------------------------------------------- KV-cached decode
-def attn_decode(kv_cache, pos_dev):
-    """kv_cache [B, Nmax, 3, H, 64] bf16 whose row *pos_dev holds the new token's q, k, v -> o [B, H*64] bf16.
-    pos_dev: int32 device tensor with one element (the position is read on the device: graph-capturable)."""
-    B, Nmax, three, H, hd = kv_cache.shape
-    if three != 3 or hd != 64:
-        raise ValueError("attn_decode: cache must be [B, Nmax, 3, H, 64]")
-    out = torch.empty(B, H * 64, device=kv_cache.device, dtype=BF16)
-    _call("b200vit_attn_decode", kv_cache, ptr(_chk(kv_cache, BF16, "kv_cache")), ptr(out), B, Nmax, H, ptr(_chk(pos_dev, torch.int32, "pos")),
-          stream_ptr())
-    return out
+def kv_cache_alloc(B, H, n_max, device):
+    """K / V planes [2, B, H, n_max, 64] bf16: one head's rows are contiguous (what the decode kernel streams)."""
+    return torch.empty(2, B, H, n_max, 64, device=device, dtype=BF16)
 
 
-def kv_append(rows, kv_cache, pos_dev):
-    """kv_cache[:, *pos_dev] = rows ([B, 3*H*64] bf16: the fused QKV projection of the new token)."""
-    B, Nmax = kv_cache.shape[0], kv_cache.shape[1]
-    row_elems = kv_cache.shape[2] * kv_cache.shape[3] * kv_cache.shape[4]
-    if rows.numel() != B * row_elems:
-        raise ValueError("kv_append: rows must be [B, 3*H*64]")
-    _call("b200vit_kv_append", rows, ptr(_chk(rows, BF16, "rows")), ptr(_chk(kv_cache, BF16, "kv_cache")), B, Nmax, row_elems,
+def kv_fill(qkv, kv_cache, B, S):
+    """kv_cache[:, :, :, :S] <- K / V of qkv [B*S, 3*H*64] (the fused QKV projection of the prompt)."""
+    _, Bc, H, n_max, _ = kv_cache.shape
+    _call("b200vit_kv_fill", qkv, ptr(_chk(qkv, BF16, "qkv")), ptr(_chk(kv_cache, BF16, "kv_cache")), B, S, n_max, H, stream_ptr())
+
+
+def kv_append(qkv_rows, kv_cache, pos_dev):
+    """kv_cache[:, :, :, *pos_dev] <- K / V of qkv_rows [B, 3*H*64] (the fused QKV projection of the new token)."""
+    _, B, H, n_max, _ = kv_cache.shape
+    if qkv_rows.numel() != B * 3 * H * 64:
+        raise ValueError("kv_append: qkv_rows must be [B, 3*H*64]")
+    _call("b200vit_kv_append", qkv_rows, ptr(_chk(qkv_rows, BF16, "qkv_rows")), ptr(_chk(kv_cache, BF16, "kv_cache")), B, n_max, H,
           ptr(_chk(pos_dev, torch.int32, "pos")), stream_ptr())
+
+
+def attn_decode(qkv_rows, kv_cache, pos_dev):
+    """One query per (batch, head) -- slot 0 of qkv_rows [B, 3*H*64] -- against the cached rows 0..*pos_dev -> o [B, H*64] bf16.
+    pos_dev: int32 device tensor with one element (the position is read on the device: graph-capturable)."""
+    two, B, H, n_max, hd = kv_cache.shape
+    if two != 2 or hd != 64:
+        raise ValueError("attn_decode: cache must be [2, B, H, Nmax, 64]")
+    out = torch.empty(B, H * 64, device=kv_cache.device, dtype=BF16)
+    _call("b200vit_attn_decode", kv_cache, ptr(_chk(qkv_rows, BF16, "qkv_rows")), ptr(_chk(kv_cache, BF16, "kv_cache")), ptr(out), B, n_max, H,
+          ptr(_chk(pos_dev, torch.int32, "pos")), stream_ptr(), hbm_bytes=float(B * H * n_max * 256))
+    return out
 
 
 def advance_counter(counter, by=1):

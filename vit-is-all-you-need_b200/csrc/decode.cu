@@ -1,58 +1,38 @@
 // Incremental (KV-cached) decode attention for VideoGPT.generate (train_videogpt.py:56-65).
 //
 // The reference re-runs the whole causal stack over the growing sequence for every generated token (O(N^2) attention
-// and O(N) GEMM work per token).  Here the keys / values of every layer stay resident in a cache with the layout of
-// the fused QKV projection output, [B, Nmax, 3, H, 64] bf16 (transformer.py:27 `(qkv h d)`), so a step appends one row
-// per layer and attends one query against the cached rows:
+// and O(N) GEMM work per token).  Here the keys / values of every layer stay resident in a per-head cache
+//     kv_cache[2][B][H][Nmax][64]  bf16      (K planes, then V planes; one head's rows are contiguous)
+// so a step appends one row per (layer, head) and attends one query against the cached rows:
 //     o[b, h, :] = softmax(q . K[0..len)^T / sqrt(64)) V[0..len)        (the new token sees itself: len = pos + 1)
 //
-// HBM-bound in bytes (len x 256 B of K and V per (batch, head), once), latency-bound in practice: a cluster of four
-// CTAs per (batch, head) splits the keys (see the kernel).  Scores: one key per thread (the query lives in registers),
-// block-wide max / sum, then P V with four value rows per warp-wide load.  fp32 math, bf16 output (the operand of the
-// following LayerNorm-add).
+// HBM-bound: one CTA per (batch, head) streams len x 256 contiguous bytes of K and V once.  The layout matters more
+// than anything else here: with the cache kept in the fused-QKV layout [B, Nmax, 3, H, 64] every key row was an isolated
+// 128-byte piece at a 4.6 KB stride and the kernel ran at ~2 TB/s (12.9 us at 520 keys, batch 16); splitting the keys over
+// 4 CTAs (plain launches + combine kernel: 16.4 us; thread-block cluster + DSMEM combine: 17.0 us) did not help.
+// Scores: one key per thread (the query lives in registers), block-wide max / sum, then P V with four value rows per
+// warp-wide load.  fp32 math, bf16 output (the operand of the following LayerNorm-add).  The position is read from
+// DEVICE memory so that one captured CUDA graph serves every step of a generation.
 #include "../../include/b200vit.h"
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 
 namespace b200 {
 
 constexpr int DEC_THREADS = 256;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
-// CTAs per (batch, head).  The kernel is written for a thread-block cluster that splits the keys and combines the
-// partials through distributed shared memory, but MEASURED on B200 (VideoGPT-B, batch 16, 520 keys): cluster of 4 x 128
-// threads 17.0 us vs one CTA of 256 threads 13.7 us per launch, and a CUDA graph whose kernel nodes carry a cluster
-// dimension replays at eager speed (1.54 instead of 0.40 ms per token) -- so the shipped configuration is 1.
-constexpr int DEC_CLUSTER = 1;
 
-// A thread-block cluster of DEC_CLUSTER CTAs serves one (batch, head): CTA r scores and weights keys
-// [r * chunk, (r + 1) * chunk) on its own (flash-decoding split), then deposits its partial (max, sum, 64 weighted
-// sums) in the leader CTA's shared memory through distributed shared memory; after one cluster barrier the leader
-// rescales and writes the output row.  The kernel is a chain of dependent memory round trips (q, keys, values), so
-// what the split buys is a four times shorter chain per CTA and four times the loads in flight per (batch, head).
 __global__ void __launch_bounds__(DEC_THREADS)
-attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __restrict__ out, int Nmax, int H,
-                   const int* __restrict__ pos_dev) {
-  namespace cg = cooperative_groups;
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  cluster.barrier_arrive();   // "I have started": waited for just before the first remote shared-memory write
-  // the position lives in device memory so that one captured CUDA graph serves every step of a generation
+attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv_rows, const __nv_bfloat16* __restrict__ cache,
+                   __nv_bfloat16* __restrict__ out, int B, int Nmax, int H, const int* __restrict__ pos_dev) {
   const int pos = min(max(__ldg(pos_dev), 0), Nmax - 1), len = pos + 1;
-  const int chunk = (len + DEC_CLUSTER - 1) / DEC_CLUSTER;
-  const int k0 = rank * chunk, k1 = min(len, k0 + chunk);     // this CTA's keys (possibly none)
-  extern __shared__ float s_scores[];                          // [ceil(Nmax / DEC_CLUSTER)]
+  extern __shared__ float s_scores[];           // [Nmax] (len used)
   __shared__ float s_red[DEC_WARPS];
   __shared__ float s_acc[DEC_WARPS][64];
-  __shared__ float s_part[DEC_CLUSTER][66];                    // leader only: per CTA {64 weighted sums, max, sum}
-  const int bh = blockIdx.x / DEC_CLUSTER;
-  const int b = bh / H, h = bh - b * H;
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row_stride = 3LL * H * 64;    // elements between consecutive positions
-  const __nv_bfloat16* base = cache + (long long)b * Nmax * row_stride + (long long)h * 64;
-  const __nv_bfloat16* qrow = base + (long long)pos * row_stride;          // slot 0: q
-  const __nv_bfloat16* kbase = base + (long long)H * 64;                   // slot 1: k
-  const __nv_bfloat16* vbase = base + 2LL * H * 64;                        // slot 2: v
+  const __nv_bfloat16* qrow = qkv_rows + (long long)b * 3 * H * 64 + h * 64;            // q of the new token
+  const __nv_bfloat16* kbase = cache + ((long long)b * H + h) * Nmax * 64;              // K plane of (b, h)
+  const __nv_bfloat16* vbase = kbase + (long long)B * H * Nmax * 64;                    // V plane of (b, h)
 
   float q[64];
 #pragma unroll
@@ -65,8 +45,8 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
   // scores in the log2 domain: (q . k) / 8 * log2(e)
   const float scale = 0.125f * 1.4426950408889634f;
   float mx = -INFINITY;
-  for (int key = k0 + threadIdx.x; key < k1; key += DEC_THREADS) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)key * row_stride);
+  for (int key = threadIdx.x; key < len; key += DEC_THREADS) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)key * 64);
     float dot = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -78,7 +58,7 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
       dot = fmaf(q[j * 8 + 6], e.x, dot); dot = fmaf(q[j * 8 + 7], e.y, dot);
     }
     dot *= scale;
-    s_scores[key - k0] = dot;
+    s_scores[key] = dot;
     mx = fmaxf(mx, dot);
   }
   mx = warp_max(mx);
@@ -88,11 +68,10 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
 #pragma unroll
   for (int w = 1; w < DEC_WARPS; ++w) mx = fmaxf(mx, s_red[w]);
   __syncthreads();
-  const float mref = mx == -INFINITY ? 0.f : mx;               // a CTA without keys contributes zeros
   float sum = 0.f;
-  for (int key = k0 + threadIdx.x; key < k1; key += DEC_THREADS) {
-    const float p = exp2f(s_scores[key - k0] - mref);
-    s_scores[key - k0] = p;
+  for (int key = threadIdx.x; key < len; key += DEC_THREADS) {
+    const float p = exp2f(s_scores[key] - mx);
+    s_scores[key] = p;
     sum += p;
   }
   sum = warp_sum(sum);
@@ -101,23 +80,23 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
   sum = 0.f;
 #pragma unroll
   for (int w = 0; w < DEC_WARPS; ++w) sum += s_red[w];
-  // P V: a warp-wide load covers 4 value rows (8 lanes x 16 B each); every lane accumulates 8 head dims of its key
-  // group, 4 loads in flight per lane; then shuffle + shared reduction
+  // P V: a warp-wide load covers 4 consecutive value rows (8 lanes x 16 B each, 512 contiguous bytes); every lane
+  // accumulates 8 head dims of its key group, 4 loads in flight per lane; then shuffle + shared reduction
   const int kg = lane >> 3, dl = lane & 7;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int key = k0 + warp * 4 + kg; key < k1; key += DEC_WARPS * 4 * 4) {
+  for (int key = warp * 4 + kg; key < len; key += DEC_WARPS * 4 * 4) {
     uint4 u[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int kk = key + i * DEC_WARPS * 4;
-      u[i] = kk < k1 ? __ldg(reinterpret_cast<const uint4*>(vbase + (long long)kk * row_stride) + dl) : make_uint4(0, 0, 0, 0);
+      u[i] = kk < len ? __ldg(reinterpret_cast<const uint4*>(vbase + (long long)kk * 64) + dl) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int kk = key + i * DEC_WARPS * 4;
-      const float p = kk < k1 ? s_scores[kk - k0] : 0.f;
+      const float p = kk < len ? s_scores[kk] : 0.f;
       const float2 v0 = unpack_bf16(u[i].x), v1 = unpack_bf16(u[i].y), v2 = unpack_bf16(u[i].z), v3 = unpack_bf16(u[i].w);
       acc[0] = fmaf(p, v0.x, acc[0]); acc[1] = fmaf(p, v0.y, acc[1]); acc[2] = fmaf(p, v1.x, acc[2]); acc[3] = fmaf(p, v1.y, acc[3]);
       acc[4] = fmaf(p, v2.x, acc[4]); acc[5] = fmaf(p, v2.y, acc[5]); acc[6] = fmaf(p, v3.x, acc[6]); acc[7] = fmaf(p, v3.y, acc[7]);
@@ -133,49 +112,44 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ cache, __nv_bfloat16* __res
     for (int i = 0; i < 8; ++i) s_acc[warp][dl * 8 + i] = acc[i];
   }
   __syncthreads();
-  // deposit this CTA's partial in the leader's shared memory (distributed shared memory), then combine there
-  cluster.barrier_wait();     // every CTA of the cluster is resident: its shared memory may be written
-  float* leader = cluster.map_shared_rank(&s_part[0][0], 0);
-  if (threadIdx.x < 64) {
-    float t = 0.f;
+  if (threadIdx.x < 32) {
+    const float inv = 1.0f / sum;
+    float o0 = 0.f, o1 = 0.f;
 #pragma unroll
-    for (int w = 0; w < DEC_WARPS; ++w) t += s_acc[w][threadIdx.x];
-    leader[rank * 66 + threadIdx.x] = t;
-  } else if (threadIdx.x == 64) {
-    leader[rank * 66 + 64] = mx;     // -inf when this CTA had no keys
-    leader[rank * 66 + 65] = sum;
-  }
-  cluster.sync();
-  if (rank == 0 && threadIdx.x < 32) {
-    float M = -INFINITY;
-#pragma unroll
-    for (int r = 0; r < DEC_CLUSTER; ++r) M = fmaxf(M, s_part[r][64]);
-    float tot = 0.f, o0 = 0.f, o1 = 0.f;
-#pragma unroll
-    for (int r = 0; r < DEC_CLUSTER; ++r) {
-      const float mr = s_part[r][64];
-      const float w = mr == -INFINITY ? 0.f : exp2f(mr - M);
-      tot = fmaf(s_part[r][65], w, tot);
-      o0 = fmaf(s_part[r][2 * lane], w, o0);
-      o1 = fmaf(s_part[r][2 * lane + 1], w, o1);
-    }
-    const float inv = 1.0f / tot;
+    for (int w = 0; w < DEC_WARPS; ++w) { o0 += s_acc[w][2 * lane]; o1 += s_acc[w][2 * lane + 1]; }
     reinterpret_cast<uint32_t*>(out + ((long long)b * H + h) * 64)[lane] = pack_bf16(o0 * inv, o1 * inv);
   }
 }
 
-// cache[b, *pos, :] = row[b, :]   (row = the new token's fused q | k | v, `row_elems` = 3 * H * 64 bf16 values)
+// K and V of the new token (slots 1 and 2 of its fused q | k | v row) -> kv_cache[{0,1}][b][h][*pos][:]
 __global__ void __launch_bounds__(256)
-kv_append_kernel(const __nv_bfloat16* __restrict__ rows, __nv_bfloat16* __restrict__ cache, int B, int Nmax, int row_elems,
+kv_append_kernel(const __nv_bfloat16* __restrict__ rows, __nv_bfloat16* __restrict__ cache, int B, int Nmax, int H,
                  const int* __restrict__ pos_dev) {
   const int pos = min(max(__ldg(pos_dev), 0), Nmax - 1);
-  const int per_row = row_elems >> 3;   // 16-byte chunks
-  const long long total = (long long)B * per_row;
+  const long long total = (long long)B * 2 * H * 8;   // 16-byte chunks: (b, k|v, h, 8 chunks of a 128-byte row)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long b = i / per_row;
-    const int c = (int)(i - b * per_row);
-    reinterpret_cast<uint4*>(cache + ((long long)b * Nmax + pos) * row_elems)[c] =
-        __ldg(reinterpret_cast<const uint4*>(rows + b * row_elems) + c);
+    const int c = (int)(i & 7);
+    const int h = (int)((i >> 3) % H);
+    const int kv = (int)((i / (8 * H)) & 1);
+    const long long b = i / (16LL * H);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rows + (b * 3 + 1 + kv) * H * 64 + h * 64) + c);
+    reinterpret_cast<uint4*>(cache + (((long long)kv * B + b) * H + h) * Nmax * 64 + (long long)pos * 64)[c] = v;
+  }
+}
+
+// prefill: qkv[B, S, 3, H, 64] (the fused QKV projection of the whole prompt) -> K / V planes [2][B][H][Nmax][64], rows 0..S
+__global__ void __launch_bounds__(256)
+kv_fill_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ cache, int B, int S, int Nmax, int H) {
+  const long long total = (long long)B * S * 2 * H * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 7);
+    const int h = (int)((i >> 3) % H);
+    const int kv = (int)((i / (8 * H)) & 1);
+    const long long bs = i / (16LL * H);
+    const long long b = bs / S;
+    const int s = (int)(bs - b * S);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(qkv + (bs * 3 + 1 + kv) * H * 64 + h * 64) + c);
+    reinterpret_cast<uint4*>(cache + (((long long)kv * B + b) * H + h) * Nmax * 64 + (long long)s * 64)[c] = v;
   }
 }
 
@@ -187,30 +161,36 @@ using namespace b200;
 
 extern "C" {
 
-int b200vit_attn_decode(const void* kv_cache, void* out_bf16, int B, int Nmax, int H, const int* pos_dev, void* stream) {
-  B200_REQUIRE(kv_cache && out_bf16 && pos_dev && B > 0 && H > 0 && Nmax > 0, "attn_decode: bad arguments");
-  const size_t smem = sizeof(float) * (size_t)((Nmax + DEC_CLUSTER - 1) / DEC_CLUSTER);
+int b200vit_attn_decode(const void* qkv_rows, const void* kv_cache, void* out_bf16, int B, int Nmax, int H, const int* pos_dev,
+                        void* stream) {
+  B200_REQUIRE(qkv_rows && kv_cache && out_bf16 && pos_dev && B > 0 && H > 0 && Nmax > 0, "attn_decode: bad arguments");
+  const size_t smem = sizeof(float) * (size_t)Nmax;
   B200_REQUIRE(smem <= 200 * 1024, "attn_decode: %d cache positions exceed the shared-memory score buffer", Nmax);
   if (smem > 40 * 1024) {
     B200_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  if (DEC_CLUSTER > 1) {
-    B200_CUDA(launch_kernel(attn_decode_kernel, dim3(B * H * DEC_CLUSTER), dim3(DEC_THREADS), smem, (cudaStream_t)stream,
-                            DEC_CLUSTER, (const __nv_bfloat16*)kv_cache, (__nv_bfloat16*)out_bf16, Nmax, H, pos_dev));
-  } else {
-    attn_decode_kernel<<<B * H, DEC_THREADS, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)kv_cache,
-                                                                          (__nv_bfloat16*)out_bf16, Nmax, H, pos_dev);
-    B200_CUDA(cudaGetLastError());
-  }
+  attn_decode_kernel<<<B * H, DEC_THREADS, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv_rows, (const __nv_bfloat16*)kv_cache,
+                                                                        (__nv_bfloat16*)out_bf16, B, Nmax, H, pos_dev);
+  B200_CUDA(cudaGetLastError());
   return OK;
 }
 
-int b200vit_kv_append(const void* rows_bf16, void* kv_cache, int B, int Nmax, int row_elems, const int* pos_dev, void* stream) {
-  B200_REQUIRE(rows_bf16 && kv_cache && pos_dev && B > 0 && Nmax > 0 && row_elems > 0 && row_elems % 8 == 0,
-               "kv_append: bad arguments (row_elems must be a multiple of 8)");
-  const long long total = (long long)B * (row_elems / 8);
-  kv_append_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)rows_bf16,
-                                                                                (__nv_bfloat16*)kv_cache, B, Nmax, row_elems, pos_dev);
+int b200vit_kv_append(const void* qkv_rows, void* kv_cache, int B, int Nmax, int H, const int* pos_dev, void* stream) {
+  B200_REQUIRE(qkv_rows && kv_cache && pos_dev && B > 0 && Nmax > 0 && H > 0, "kv_append: bad arguments");
+  const long long total = (long long)B * 2 * H * 8;
+  kv_append_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv_rows,
+                                                                                (__nv_bfloat16*)kv_cache, B, Nmax, H, pos_dev);
+  B200_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int b200vit_kv_fill(const void* qkv, void* kv_cache, int B, int S, int Nmax, int H, void* stream) {
+  B200_REQUIRE(qkv && kv_cache && B > 0 && S > 0 && S <= Nmax && H > 0, "kv_fill: bad arguments (S <= Nmax)");
+  const long long total = (long long)B * S * 2 * H * 8;
+  const long long want = (total + 255) / 256;
+  const int cap = num_sms() * 16;
+  kv_fill_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kv_cache,
+                                                                                  B, S, Nmax, H);
   B200_CUDA(cudaGetLastError());
   return OK;
 }
