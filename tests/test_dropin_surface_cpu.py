@@ -110,3 +110,18 @@ def test_launcher_swaps_classes_and_keeps_state_dict_contract():
     assert ours["vqgan"] == ref["vqgan"], "ViTVQGAN (train_vit_vqgan.py) state_dict keys/shapes must equal the reference's"
     assert all(c.startswith("b200vit") for c in ours["classes"]), ours["classes"]
     assert not any(c.startswith("b200vit") for c in ref["classes"])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_unchanged_reference_script_runs_to_the_kernel_boundary(tmp_path):
+    """`python -m b200vit.launch <reference>/train_vit.py ...` with the script UNCHANGED: imports resolve to the drop-ins,
+    the model / optimizer / loss are built, the first forward reaches the C ABI -- and, on this GPU-less container, fails
+    loudly there instead of falling back to PyTorch."""
+    env = dict(os.environ, B200VIT_SYNTHETIC="1", B200VIT_SYNTHETIC_SAMPLES="4", PYTHONPATH=PKG, WANDB_MODE="disabled")
+    r = subprocess.run([sys.executable, "-m", "b200vit.launch", os.path.join(REF, "train_vit.py"), "--transformer", "S",
+                        "--image_size", "32", "--patch_size", "4", "--bs", "2", "--epochs", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path), env=env)
+    out = r.stdout + r.stderr
+    assert "STATS: params=" in out, out[-1500:]                 # the script got as far as building everything
+    if not torch.cuda.is_available():
+        assert r.returncode != 0 and "no CPU fallback" in out, out[-1500:]
