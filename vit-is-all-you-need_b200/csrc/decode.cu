@@ -10,8 +10,8 @@
 // than anything else here: with the cache kept in the fused-QKV layout [B, Nmax, 3, H, 64] every key row was an isolated
 // 128-byte piece at a 4.6 KB stride and the kernel ran at ~2 TB/s (12.9 us at 520 keys, batch 16); splitting the keys over
 // 4 CTAs (plain launches + combine kernel: 16.4 us; thread-block cluster + DSMEM combine: 17.0 us) did not help.
-// Scores: one key per thread (the query lives in registers), block-wide max / sum, then P V with four value rows per
-// warp-wide load.  fp32 math, bf16 output (the operand of the following LayerNorm-add).  The position is read from
+// Scores and P V both read four consecutive rows per warp-wide load (8 lanes x 16 B per row), block-wide max / sum in
+// between.  fp32 math, bf16 output (the operand of the following LayerNorm-add).  The position is read from
 // DEVICE memory so that one captured CUDA graph serves every step of a generation.
 #include "../../include/b200vit.h"
 #include "common.cuh"
@@ -34,32 +34,45 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv_rows, const __nv_bfloat
   const __nv_bfloat16* kbase = cache + ((long long)b * H + h) * Nmax * 64;              // K plane of (b, h)
   const __nv_bfloat16* vbase = kbase + (long long)B * H * Nmax * 64;                    // V plane of (b, h)
 
-  float q[64];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(qrow) + j);
+  // Scores, coalesced: 8 lanes share one key row (16 bytes each), so a warp-wide load covers 4 consecutive rows = 512
+  // contiguous bytes (a thread-per-row scheme touches 32 different 128-byte lines per load instruction and is bound by
+  // L1 tag throughput); partial dot products are reduced over the 8 lanes with 3 shuffles.  8 loads in flight per lane.
+  const int kg = lane >> 3, dl = lane & 7;
+  float qf[8];
+  {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(qrow) + dl);
     const float2 a = unpack_bf16(u.x), c = unpack_bf16(u.y), d = unpack_bf16(u.z), e = unpack_bf16(u.w);
-    q[j * 8 + 0] = a.x; q[j * 8 + 1] = a.y; q[j * 8 + 2] = c.x; q[j * 8 + 3] = c.y;
-    q[j * 8 + 4] = d.x; q[j * 8 + 5] = d.y; q[j * 8 + 6] = e.x; q[j * 8 + 7] = e.y;
+    qf[0] = a.x; qf[1] = a.y; qf[2] = c.x; qf[3] = c.y; qf[4] = d.x; qf[5] = d.y; qf[6] = e.x; qf[7] = e.y;
   }
   // scores in the log2 domain: (q . k) / 8 * log2(e)
   const float scale = 0.125f * 1.4426950408889634f;
   float mx = -INFINITY;
-  for (int key = threadIdx.x; key < len; key += DEC_THREADS) {
-    const uint4* kr = reinterpret_cast<const uint4*>(kbase + (long long)key * 64);
-    float dot = 0.f;
+  constexpr int QK_ILP = 8;
+  // (warp-uniform trip count: the shuffles below need all 32 lanes; invalid keys are predicated inside)
+  for (int base = warp * 4; base < len; base += DEC_WARPS * 4 * QK_ILP) {
+    const int key = base + kg;
+    uint4 u[QK_ILP];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint4 u = __ldg(kr + j);
-      const float2 a = unpack_bf16(u.x), c = unpack_bf16(u.y), d = unpack_bf16(u.z), e = unpack_bf16(u.w);
-      dot = fmaf(q[j * 8 + 0], a.x, dot); dot = fmaf(q[j * 8 + 1], a.y, dot);
-      dot = fmaf(q[j * 8 + 2], c.x, dot); dot = fmaf(q[j * 8 + 3], c.y, dot);
-      dot = fmaf(q[j * 8 + 4], d.x, dot); dot = fmaf(q[j * 8 + 5], d.y, dot);
-      dot = fmaf(q[j * 8 + 6], e.x, dot); dot = fmaf(q[j * 8 + 7], e.y, dot);
+    for (int i = 0; i < QK_ILP; ++i) {
+      const int kk = key + i * DEC_WARPS * 4;
+      u[i] = kk < len ? __ldg(reinterpret_cast<const uint4*>(kbase + (long long)kk * 64) + dl) : make_uint4(0, 0, 0, 0);
     }
-    dot *= scale;
-    s_scores[key] = dot;
-    mx = fmaxf(mx, dot);
+#pragma unroll
+    for (int i = 0; i < QK_ILP; ++i) {
+      const int kk = key + i * DEC_WARPS * 4;
+      const float2 a = unpack_bf16(u[i].x), c = unpack_bf16(u[i].y), d = unpack_bf16(u[i].z), e = unpack_bf16(u[i].w);
+      float dot = qf[0] * a.x;
+      dot = fmaf(qf[1], a.y, dot); dot = fmaf(qf[2], c.x, dot); dot = fmaf(qf[3], c.y, dot);
+      dot = fmaf(qf[4], d.x, dot); dot = fmaf(qf[5], d.y, dot); dot = fmaf(qf[6], e.x, dot); dot = fmaf(qf[7], e.y, dot);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      if (kk < len) {
+        dot *= scale;
+        if (dl == 0) s_scores[kk] = dot;
+        mx = fmaxf(mx, dot);
+      }
+    }
   }
   mx = warp_max(mx);
   if (lane == 0) s_red[warp] = mx;
@@ -81,20 +94,20 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv_rows, const __nv_bfloat
 #pragma unroll
   for (int w = 0; w < DEC_WARPS; ++w) sum += s_red[w];
   // P V: a warp-wide load covers 4 consecutive value rows (8 lanes x 16 B each, 512 contiguous bytes); every lane
-  // accumulates 8 head dims of its key group, 4 loads in flight per lane; then shuffle + shared reduction
-  const int kg = lane >> 3, dl = lane & 7;
+  // accumulates 8 head dims of its key group, 8 loads in flight per lane; then shuffle + shared reduction
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int key = warp * 4 + kg; key < len; key += DEC_WARPS * 4 * 4) {
-    uint4 u[4];
+  constexpr int PV_ILP = 8;
+  for (int key = warp * 4 + kg; key < len; key += DEC_WARPS * 4 * PV_ILP) {
+    uint4 u[PV_ILP];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < PV_ILP; ++i) {
       const int kk = key + i * DEC_WARPS * 4;
       u[i] = kk < len ? __ldg(reinterpret_cast<const uint4*>(vbase + (long long)kk * 64) + dl) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < PV_ILP; ++i) {
       const int kk = key + i * DEC_WARPS * 4;
       const float p = kk < len ? s_scores[kk] : 0.f;
       const float2 v0 = unpack_bf16(u[i].x), v1 = unpack_bf16(u[i].y), v2 = unpack_bf16(u[i].z), v3 = unpack_bf16(u[i].w);
