@@ -49,3 +49,19 @@ def test_product_package_never_touches_the_oracle():
             if re.search(r"^\s*(from|import)\s+oracle\b", line) or "oracle/" in line and "subprocess" in line:
                 offenders.append(f"{path}:{n}")
     assert not offenders, offenders
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/b200vit.h is a C ABI: it must compile as C99 with nothing but the standard headers."""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "b200vit.h"\nint (*probe)(void) = b200vit_version;\nint main(void) { return probe == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-c", str(src), "-I", os.path.join(root, "include"), "-o",
+                        str(tmp_path / "hdr.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
