@@ -205,7 +205,7 @@ class TransformerStackFn(torch.autograd.Function):
     def backward(ctx, dy):
         B, N, d, H, causal = ctx.dims
         dx = _as_rows_f32(dy).view(B * N, d)
-        twin = getattr(dy, "_b200_bf16_twin", None)   # ClassifierHeadFn.backward hands the bf16 copy along
+        twin = getattr(dy, "_b200_bf16_twin", None)   # TokenLinearFn / DepatchifyFn backward hand the bf16 copy along
         dx_bf16 = None
         if twin is not None and twin[1] == dy._version and dy.dtype == F32 and dy.is_contiguous() and twin[0].shape == dy.shape:
             dx_bf16 = twin[0].view(B * N, d)
