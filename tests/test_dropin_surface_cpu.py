@@ -125,3 +125,28 @@ def test_unchanged_reference_script_runs_to_the_kernel_boundary(tmp_path):
     assert "STATS: params=" in out, out[-1500:]                 # the script got as far as building everything
     if not torch.cuda.is_available():
         assert r.returncode != 0 and "no CPU fallback" in out, out[-1500:]
+
+
+def test_operand_cache_epoch_and_launcher_swaps_on_cpu():
+    """Host logic that needs no GPU: (1) ANY optimizer step invalidates the bf16 operand caches (torch's fused optimisers do
+    not bump Tensor._version); (2) the launcher's loss / optimizer swaps install the drop-ins and leave unsupported uses to
+    torch (CPU tensors here)."""
+    import torch.nn.functional as F
+    from b200vit import functional as Fn
+    from b200vit import launch, optim
+    p = torch.nn.Parameter(torch.randn(8))
+    p.grad = torch.randn(8)
+    k0 = Fn.bf16_key(p)
+    torch.optim.SGD([p], lr=0.1).step()
+    k1 = Fn.bf16_key(p)
+    assert k1 != k0 and k1[0] == k0[0] + 1                       # the epoch advanced (and the version, for SGD)
+    orig_ce, orig_adamw = F.cross_entropy, torch.optim.AdamW
+    try:
+        launch.install_loss_swap()
+        launch.install_optimizer_swap()
+        assert torch.optim.AdamW is optim.AdamW
+        x, y = torch.randn(5, 7), torch.randint(0, 7, (5,))
+        torch.testing.assert_close(F.cross_entropy(x, y), orig_ce(x, y))                       # CPU: torch's path
+        torch.testing.assert_close(torch.nn.CrossEntropyLoss(label_smoothing=0.1)(x, y), orig_ce(x, y, label_smoothing=0.1))
+    finally:
+        F.cross_entropy, torch.optim.AdamW = orig_ce, orig_adamw
