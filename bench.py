@@ -2,7 +2,7 @@
 """ViT-B/16 224px bf16 training throughput on 1..8 B200s (BASELINE.json configs[1]) through the drop-in modules.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]        # our arm
-    python bench.py --impl reference ...                                    # the reference's CPU path (oracle port)
+    python bench.py --impl reference ...      # the reference's own CPU path (unmodified modules from baseline/_ref)
 
 One "step" = forward + cross-entropy + backward + AdamW on a per-GPU batch of synthetic images (weak scaling).
 `value` is measured with the inputs already resident in HBM; `e2e` runs the same step from pinned HOST buffers
@@ -171,23 +171,107 @@ def cpu_reference_step_rate(batch, steps, warmup):
     return batch / dt, dt
 
 
+def _reference_vit_b(torch, device):
+    """The UNMODIFIED reference model of configs[1] (train_vit.py:30-53 from baseline/_ref) with its own default init."""
+    from baseline import loader
+    ref = loader.load(("transformer", "train_vit"))
+    torch.manual_seed(0)
+    cfg = ref.train_vit.ViTConfig(IMAGE, 3, PATCH, "B", 1, 0.0)
+    return ref.train_vit.ViTClassifier(cfg, num_classes=CLASSES).to(device)
+
+
+def cpu_true_reference_step_rate(batch, steps, warmup):
+    """The reference's own CPU path: train_vit.py:99-105 (forward under autocast("cuda") -- which disables itself without a
+    GPU, i.e. fp32 --, CrossEntropyLoss, backward, torch.optim.AdamW) through the unmodified modules, all host threads
+    (torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly).  Returns (images/s, s/step, threads)."""
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = _reference_vit_b(torch, "cpu")
+    optim = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 3, IMAGE, IMAGE, generator=g)
+    y = torch.randint(0, CLASSES, (batch,), generator=g)
+
+    def one_step():
+        optim.zero_grad()
+        loss = loss_fn(model(x), y)
+        loss.backward()
+        optim.step()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt, torch.get_num_threads()
+
+
+def gpu_eager_reference_step_rate(torch, device, batch, steps, warmup):
+    """Same-box GPU comparator (SURVEY.md §8d, §2b "the kernel to beat"): the UNMODIFIED reference modules on this B200 through
+    PyTorch eager -- cuBLASLt GEMMs, cuDNN conv, ATen LayerNorm / GELU / SDPA -- under torch.autocast("cuda", torch.bfloat16),
+    torch.optim.AdamW(fused=True); the step of train_vit.py:99-105 at the bench batch, device-resident inputs, CUDA events."""
+    model = _reference_vit_b(torch, device)
+    optim = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2, fused=True)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 3, IMAGE, IMAGE, generator=g).to(device)
+    y = torch.randint(0, CLASSES, (batch,), generator=g).to(device)
+
+    def one_step():
+        optim.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = loss_fn(model(x), y)
+        loss.backward()
+        optim.step()
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, optim
+    torch.cuda.empty_cache()
+    return batch / (ms / 1e3), ms
+
+
+def cpu_baseline_sample(batch, steps, warmup):
+    """(images/s, s/step, cores, kind, description): the unmodified reference when baseline/_ref is present, else the
+    numpy oracle port."""
+    from baseline import loader
+    if loader.available():
+        ips, dt, threads = cpu_true_reference_step_rate(batch, steps, warmup)
+        return ips, dt, threads, "reference", (f"{steps} step(s) of batch {batch} after {warmup} warm-up (ViT-B/16 224, fwd+CE+bwd+AdamW, "
+                                               f"unmodified reference modules train_vit.py:30-53 on CPU fp32, torch {threads} threads)")
+    ips, dt = cpu_reference_step_rate(batch, steps, warmup)
+    return ips, dt, os.cpu_count(), "port", f"{steps} step(s) of batch {batch} (ViT-B/16 224, fwd+CE+bwd+AdamW, fp32 numpy oracle port)"
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     batch = args.cpu_batch
-    steps = max(1, min(args.steps, 3))
+    steps = max(1, min(args.steps, 4))
     warm = 1 if args.warmup > 0 else 0
-    ips, dt = cpu_reference_step_rate(batch, steps, warm)
-    cores = os.cpu_count()
+    ips, dt, cores, kind, sample = cpu_baseline_sample(batch, steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ViT-B/16 224px train step (fwd + CE + bwd + AdamW), reference CPU path (numpy oracle port)",
-                   "global_batch": batch, "parallelism": "cpu"},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} step(s) of batch {batch} (ViT-B/16 224, fwd+CE+bwd+AdamW, fp32 numpy/BLAS)"},
+        "config": {"workload": "ViT-B/16 224px ImageNet-shape train step (fwd + CE + bwd + AdamW), configs[1]",
+                   "arm": ("the reference's own CPU path (unmodified modules from baseline/_ref)" if kind == "reference"
+                           else "numpy oracle port of the reference (baseline/_ref absent)"),
+                   "sample_batch": batch, "parallelism": "cpu"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -365,12 +449,21 @@ def run_gpu_arm(args):
                         "detail": {k.replace("b200vit_", ""): {"GBps": v["rate"] / 1e9, "launches": v["launches"], "ms_per_step": v["ms"] / 2} for k, v in ln_detail.items()}},
         "final_loss": losses[-1] if losses else None,
     }
+    if world == 1 and not args.no_gpu_eager_baseline:
+        from baseline import loader as _ref_loader
+        if _ref_loader.available():
+            del model, wrapped, optim
+            torch.cuda.empty_cache()
+            eips, ems = gpu_eager_reference_step_rate(torch, device, B, min(args.steps, 10), 3)
+            line["gpu_eager_baseline"] = {
+                "value": eips, "unit": UNIT, "ms_per_step": ems, "speedup_of_this_repo": ips / eips,
+                "what": "unmodified reference modules (baseline/_ref train_vit.ViTClassifier) on the same B200: PyTorch eager under "
+                        "torch.autocast('cuda', bfloat16) + torch.optim.AdamW(fused=True), same batch, device-resident inputs"}
+        else:
+            line["gpu_eager_baseline"] = {"unavailable": "baseline/_ref absent"}
     if world == 1 and not args.no_cpu_baseline:
-        cb = args.cpu_batch
-        csteps = 3
-        cips, cdt = cpu_reference_step_rate(cb, csteps, 0)
-        line["cpu_baseline"] = {"value": cips, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{csteps} steps of batch {cb} (ViT-B/16 224, fwd+CE+bwd+AdamW, fp32 numpy oracle, {cdt * csteps:.1f} s in total)"}
+        cips, cdt, ccores, ckind, csample = cpu_baseline_sample(args.cpu_batch, 3, 1)
+        line["cpu_baseline"] = {"value": cips, "unit": UNIT, "cores": ccores, "kind": ckind, "sample": csample}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -383,8 +476,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
     ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--impl", type=str, default="b200vit", choices=["b200vit", "reference"])
-    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU-baseline sample (one step is ~4 s on 16 cores)")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU-baseline sample (a few seconds per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="ViTConfig.dropout (SDPA dropout_p + nn.Dropout after mlp[2]); train_vit.py's own default is 0.15. "
                          "The headline number is measured at 0.0 (BASELINE configs[1]); other values are for throughput only")

@@ -1,5 +1,6 @@
-"""bench.py contract that can be checked without a GPU: the reference arm (the reference's CPU path == the numpy
-oracle port) prints ONE JSON line with the agreed keys, and the GPU arm refuses to run silently on CPU."""
+"""bench.py contract that can be checked without a GPU: the reference arm (the reference's own CPU path: the unmodified
+modules from baseline/_ref; the numpy oracle port only when that copy is absent) prints ONE JSON line with the agreed keys,
+also under torchrun's OMP_NUM_THREADS=1, and the GPU arm refuses to run silently on CPU."""
 import json
 import os
 import subprocess
@@ -9,15 +10,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line():
+    env = dict(os.environ, OMP_NUM_THREADS="1")       # what torch.distributed.run exports to every rank
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-batch", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--cpu-batch", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "vit_b16_224_train_images_per_sec" and d["unit"] == "images/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["dtype"] == "f32"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    sys.path.insert(0, ROOT)
+    from baseline import loader
+    assert d["cpu_baseline"]["kind"] == ("reference" if loader.available() else "port")
+    assert d["cpu_baseline"]["cores"] == (os.cpu_count() if loader.available() else d["cpu_baseline"]["cores"])   # not 1 under torchrun
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 

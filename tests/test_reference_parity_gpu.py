@@ -71,10 +71,11 @@ def _run(model, step, amp, extras=None):
     if amp:
         with torch.autocast("cuda", dtype=torch.bfloat16):
             outs, loss = step(model)
+        loss.backward()
     else:
-        with _NoTF32():
+        with _NoTF32():      # backward too: its matmuls read the TF32 switch when they run
             outs, loss = step(model)
-    loss.backward()
+            loss.backward()
     torch.cuda.synchronize()
     outs = [o.detach().float() for o in outs]
     if extras is not None:          # tensors only available after backward (input gradients)

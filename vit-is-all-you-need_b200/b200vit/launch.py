@@ -14,7 +14,15 @@ What it does:
     same constructor, state_dict layout and GradScaler protocol; B200VIT_TORCH_ADAMW=1 keeps torch's);
   * F.cross_entropy (and with it nn.CrossEntropyLoss) takes the fused cross-entropy kernels for 2-D CUDA logits;
   * stubs two imports the scripts never use (lpips, vector_quantize_pytorch.FSQ) when they are not installed,
-    disables wandb, and (B200VIT_SYNTHETIC=1) replaces the hard-coded ImageNet loaders with synthetic ones.
+    disables wandb, and (B200VIT_SYNTHETIC=1) replaces the hard-coded ImageNet loaders with synthetic ones and
+    perceptual_loss.PerceptualLoss (torchvision ConvNeXt-S whose ImageNet weights are a network download,
+    perceptual_loss.py:41) with a small frozen, seeded feature network of the same interface.
+
+Harness knobs (none of them changes what the script computes):
+    B200VIT_SEED=<int>        torch.manual_seed before the script starts (the scripts never seed)
+    B200VIT_LOG_JSONL=<path>  every wandb.log({...}) call of the script also appends its scalar entries as one JSON line
+    B200VIT_PLAIN=1           install only the harness pieces (stubs, synthetic data, log, seed) and NOT the drop-ins: the
+                              un-accelerated comparison run of tests/test_scripts_gpu.py
 """
 import builtins
 import os
@@ -38,6 +46,10 @@ def install_import_shims(reference_dir):
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, SHIM)  # shim first: bare `transformer`, `train_vit`, `blocks` resolve here
     os.environ.setdefault("WANDB_MODE", "disabled")
+    _stub_unused_imports()
+
+
+def _stub_unused_imports():
     try:
         import lpips  # noqa: F401
     except Exception:
@@ -140,19 +152,111 @@ def install_synthetic_loaders():
     datasets.get_imagenet_loaders = get_imagenet_loaders
 
 
+def install_perceptual_loss_stub():
+    """perceptual_loss.PerceptualLoss (perceptual_loss.py:27-70) needs torchvision's ConvNeXt-S ImageNet weights, a network
+    download (perceptual_loss.py:41).  Synthetic runs get a module of the same interface -- frozen, eval-mode, inputs in
+    [0, 1] resized to a fixed square, feature MSE -- over a small seeded convolutional network (out of scope for the hot
+    path, SURVEY.md §2 #18; plain torch, identical in the accelerated and the plain run)."""
+    import torch
+
+    class PerceptualLoss(torch.nn.Module):
+        def __init__(self, model_name: str = "convnext_s"):
+            super().__init__()
+            if "convnext_s" not in model_name:
+                raise ValueError(f"Unsupported Perceptual Loss model name {model_name}")
+            conv = torch.nn.Conv2d     # padded 3x3 / 4x4 convolutions: PatchConv2d (if installed) passes them through
+            with torch.random.fork_rng(devices=[]):
+                torch.manual_seed(20260101)
+                self.features = torch.nn.Sequential(
+                    conv(3, 32, 4, stride=4, padding=1), torch.nn.GELU(),
+                    conv(32, 64, 3, stride=2, padding=1), torch.nn.GELU(),
+                    conv(64, 128, 3, stride=2, padding=1), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(),
+                    torch.nn.Linear(128, 1000))
+            self.register_buffer("imagenet_mean", torch.tensor([0.485, 0.456, 0.406])[None, :, None, None])
+            self.register_buffer("imagenet_std", torch.tensor([0.229, 0.224, 0.225])[None, :, None, None])
+            for p in self.parameters():
+                p.requires_grad = False
+
+        def forward(self, input, target):
+            self.eval()
+            F = torch.nn.functional
+            input = F.interpolate(input.float(), size=64, mode="bilinear", align_corners=False, antialias=True)
+            target = F.interpolate(target.float(), size=64, mode="bilinear", align_corners=False, antialias=True)
+            a = self.features((input - self.imagenet_mean) / self.imagenet_std)
+            b = self.features((target - self.imagenet_mean) / self.imagenet_std)
+            return F.mse_loss(a, b, reduction="mean")
+
+    m = types.ModuleType("perceptual_loss")
+    m.PerceptualLoss = PerceptualLoss
+    m.__doc__ = "synthetic stand-in installed by b200vit.launch (B200VIT_SYNTHETIC=1)"
+    sys.modules["perceptual_loss"] = m
+
+
+def install_log_hook(path):
+    """wandb.log is the scripts' only record of the loss (train_vit.py:109, train_titok.py:167); mirror its scalars to a file."""
+    import json
+
+    import wandb
+
+    def log(data=None, *a, **k):
+        try:
+            row = {}
+            for key, v in (data or {}).items():
+                if hasattr(v, "item") and getattr(v, "numel", lambda: 1)() == 1:
+                    v = v.item()
+                if isinstance(v, (int, float)):
+                    row[key] = v
+            if row:
+                with open(path, "a") as f:
+                    f.write(json.dumps(row) + "\n")
+        except Exception:   # pragma: no cover  (logging must never break the run)
+            pass
+        return log.inner(data, *a, **k)
+
+    log.inner = wandb.log
+    orig_init = wandb.init
+
+    def init(*a, **k):      # wandb.init() re-binds the module-level wandb.log to the new run: wrap it again afterwards
+        run = orig_init(*a, **k)
+        if wandb.log is not log:
+            log.inner = wandb.log
+            wandb.log = log
+        return run
+
+    wandb.init = init
+    wandb.log = log
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
         raise SystemExit(__doc__)
     script = os.path.abspath(argv[0])
-    install_import_shims(os.path.dirname(script))
+    plain = os.environ.get("B200VIT_PLAIN", "0") == "1"
+    if plain:
+        ref_dir = os.path.dirname(script)
+        if ref_dir in sys.path:
+            sys.path.remove(ref_dir)
+        sys.path.insert(0, ref_dir)
+        os.environ.setdefault("WANDB_MODE", "disabled")
+        _stub_unused_imports()
+    else:
+        install_import_shims(os.path.dirname(script))
     if os.environ.get("B200VIT_SYNTHETIC", "0") == "1":
         install_synthetic_loaders()
-    orig = install_class_swap()
-    install_conv_swap()
-    if os.environ.get("B200VIT_TORCH_ADAMW", "0") != "1":
-        install_optimizer_swap()
-    install_loss_swap()
+        install_perceptual_loss_stub()
+    if os.environ.get("B200VIT_LOG_JSONL"):
+        install_log_hook(os.environ["B200VIT_LOG_JSONL"])
+    orig = builtins.__build_class__
+    if not plain:
+        orig = install_class_swap()
+        install_conv_swap()
+        if os.environ.get("B200VIT_TORCH_ADAMW", "0") != "1":
+            install_optimizer_swap()
+        install_loss_swap()
+    if os.environ.get("B200VIT_SEED"):
+        import torch
+        torch.manual_seed(int(os.environ["B200VIT_SEED"]))
     sys.argv = [script] + argv[1:]
     try:
         runpy.run_path(script, run_name="__main__")
