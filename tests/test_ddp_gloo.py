@@ -37,11 +37,14 @@ class _SinkLinear(torch.autograd.Function):
         from b200vit import functional as Fn
         x, w = ctx.saved_tensors
         gw = dy.t() @ x
-        slot = Fn._slot(ctx.sink, ctx.w)
+        if getattr(_SinkLinear, "fail_next", False):
+            _SinkLinear.fail_next = False
+            raise RuntimeError("injected backward failure")
+        slot = Fn._slot(ctx.sink, ctx.w)      # asked once; None -> the gradient goes through autograd (functional.layer_backward)
         if slot is not None:
             slot.copy_(gw)
             gw = None   # delivered through the sink: autograd gets no second copy
-        Fn._ready(ctx.sink, ctx.w)
+            Fn._ready(ctx.sink, ctx.w)
         return dy @ w, gw
 
 
@@ -98,8 +101,8 @@ def _worker(rank, world, port, tmpdir):
                 continue
             assert p.grad is not None
             torch.testing.assert_close(p.grad, e, rtol=1e-5, atol=1e-6)
-            slot = model.grad_slot(p)
-            assert p.grad.data_ptr() == slot.data_ptr(), "param.grad must alias its bucket slot"
+            assert model.grad_slot(p) is None, "a populated .grad must not be offered for overwriting"
+            assert p.grad.data_ptr() == model._slots[p][1].data_ptr(), "param.grad must alias its bucket slot"
         # an un-wrapped model trained in the same process (teacher, second network ...) is not routed into the sink
         other, _, _ = local_grads(rank)
         assert other[0] is not None
@@ -112,6 +115,29 @@ def _worker(rank, world, port, tmpdir):
         ((model(x) - y) ** 2).mean().backward()
     idx_w = [n for n, _ in net.named_parameters()].index("w")
     torch.testing.assert_close(net.w.grad, per_rank[rank][0][idx_w], rtol=1e-5, atol=1e-6)
+
+    # gradient accumulation: a no_sync() micro-step (above) followed by a synchronised step must reduce the SUM of both
+    # micro-step gradients for sink-delivered (w) and hook-delivered (a, b) parameters alike
+    ((model(x) - y) ** 2).mean().backward()
+    for (name, p), e in zip(net.named_parameters(), expect):
+        if e is not None:
+            torch.testing.assert_close(p.grad, 2 * e, rtol=1e-5, atol=1e-6, msg=lambda m, n=name: f"accumulated {n}: {m}")
+
+    # a backward that raises must not leave the wrapper stuck: the next step reduces normally
+    for p in net.parameters():
+        p.grad = None
+    _SinkLinear.fail_next = True
+    try:
+        ((model(x) - y) ** 2).mean().backward()
+        raise AssertionError("the injected failure did not surface")
+    except RuntimeError as err:
+        assert "injected" in str(err)
+    for p in net.parameters():
+        p.grad = None
+    ((model(x) - y) ** 2).mean().backward()
+    for (name, p), e in zip(net.named_parameters(), expect):
+        if e is not None:
+            torch.testing.assert_close(p.grad, e, rtol=1e-5, atol=1e-6, msg=lambda m, n=name: f"after a failed backward {n}: {m}")
     dist.destroy_process_group()
     open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
 

@@ -453,6 +453,14 @@ def test_cross_entropy_strided_logits_and_all_ignored(ops):
     assert abs(float(loss[0]) - float(ref)) < 1e-5
     loss, _ = ops.cross_entropy_fwd(xd, to_dev(np.full(9, -100, dtype=np.int64)))
     assert math.isnan(float(loss[0])) and float(loss[1]) == 0.0   # torch: mean over zero rows is nan
+    # a label outside [0, C) that is not ignore_index: torch raises a device assert; here the loss AND the gradient scale
+    # are poisoned with NaN (no host sync), so a label / class-count mismatch cannot train silently
+    bad = y.copy()
+    bad[4] = 10
+    loss, lse = ops.cross_entropy_fwd(xd, to_dev(bad))
+    assert math.isnan(float(loss[0])) and math.isnan(float(loss[1]))
+    dx = ops.cross_entropy_bwd(xd.contiguous(), to_dev(bad), lse, loss, torch.ones(1, device=DEV))
+    assert torch.isnan(dx[0]).all()
 
 
 @pytest.mark.parametrize("B,N,d,t0,cnt", [(5, 65, 192, 0, 1), (3, 197, 768, 0, 1), (4, 7, 64, 3, 1), (3, 288, 512, 0, 32),

@@ -183,3 +183,40 @@ def test_adamw_skips_parameters_without_gradients_and_handles_changing_sets():
     b1, _, _, _ = A.adamw_step(b0, gb, np.zeros_like(b0), np.zeros_like(b0), 1, 1e-2)
     _close(b, b1, "b after its first step")
     assert float(opt.state[a]["step"]) == 1.0 and float(opt.state[b]["step"]) == 1.0
+
+
+def test_adamw_refuses_graph_capture_without_capturable_and_keeps_host_steps_on_the_host():
+    """(1) capturing step() with a host-side step counter would freeze the bias corrections into the graph: refused, like
+    torch's _cuda_graph_capture_health_check.  (2) load_state_dict must not leave `step` on the device for non-capturable
+    groups (one .item() sync per parameter and step otherwise) and the trajectory continues exactly."""
+    from b200vit.graph import GraphedTrainStep
+    from b200vit.optim import AdamW
+    rng = np.random.default_rng(5)
+    w0 = rng.standard_normal(1000).astype(np.float32)
+    gs = [rng.standard_normal(1000).astype(np.float32) for _ in range(4)]
+
+    def run(reload_after):
+        p = torch.nn.Parameter(torch.from_numpy(w0).to(DEV))
+        opt = AdamW([p], lr=1e-2)
+        for i, g in enumerate(gs):
+            p.grad = torch.from_numpy(g).to(DEV)
+            opt.step()
+            if i == reload_after:
+                sd = opt.state_dict()
+                opt = AdamW([p], lr=1e-2)
+                opt.load_state_dict(sd)
+                assert opt.state[p]["step"].device.type == "cpu" and float(opt.state[p]["step"]) == i + 1
+        return p.detach().cpu().numpy()
+
+    assert np.array_equal(run(None), run(1))
+    p = torch.nn.Parameter(torch.from_numpy(w0).to(DEV))
+    opt = AdamW([p], lr=1e-2)
+    p.grad = torch.from_numpy(gs[0]).to(DEV)
+    opt.step()
+    graph = torch.cuda.CUDAGraph()
+    with pytest.raises(RuntimeError, match="capturable=True"):
+        with torch.cuda.graph(graph):
+            opt.step()
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError, match="capturable=True"):
+        GraphedTrainStep(torch.nn.Linear(4, 4).to(DEV), opt, None, torch.zeros(1, 4, device=DEV), torch.zeros(1, device=DEV))

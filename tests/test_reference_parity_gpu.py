@@ -12,7 +12,7 @@ Three runs per configuration from the same state_dict and inputs:
     ours     the drop-in under the same autocast (hand-written sm_100a kernels)
 and three checks on the outputs, the loss and EVERY parameter gradient:
     (1) absolute:  |loss - anchor| <= LOSS_TOL * |anchor|;  output rel-L2 <= OUT_TOL;  gradient rel-L2 <= GRAD_TOL and
-        cosine >= GRAD_COS  (SURVEY.md §8c tolerances, widened for 12-24 layers of bf16 error growth -- values below);
+        cosine >= GRAD_COS  (SURVEY.md §8c tolerances -- values below);
     (2) relative:  ours' error against the anchor is no worse than SLACK x the reference's own bf16 error (+ a floor);
     (3) the VQ indices are bit-exact when both quantisers are fed identical fp32 latents.
 Skipped (not failed) when baseline/_ref is absent."""
@@ -26,12 +26,14 @@ from baseline import loader
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not loader.available(), reason="baseline/_ref (reference copy) not present")]
 DEV = "cuda:0"
 
-LOSS_TOL = 2e-2      # relative
-OUT_TOL = 3e-2       # rel-L2 of logits / tokens / reconstructed image after a full stack
-GRAD_TOL = 6e-2      # rel-L2 of a parameter gradient (deep stacks: the first layers see 12-24 layers of bf16 backward error)
-GRAD_COS = 0.998
-SLACK = 1.6          # ours' error <= SLACK * (reference-under-bf16-autocast error) + FLOOR
-FLOOR = 4e-3
+# SURVEY.md §8c tolerances; measured on a B200 (profiles/r2_parity_fullsize.md): outputs 3-4e-3, gradients 1.4e-3 .. 6e-3
+# (codebook 1.4e-2), cosines >= 0.99991, and ours <= 1.05 x the reference's own bf16 error on every tensor
+LOSS_TOL = 5e-3      # relative
+OUT_TOL = 1e-2       # rel-L2 of logits / tokens / reconstructed image after a full stack
+GRAD_TOL = 2e-2      # rel-L2 of a parameter gradient
+GRAD_COS = 0.999
+SLACK = 1.3          # ours' error <= SLACK * (reference-under-bf16-autocast error) + FLOOR
+FLOOR = 2e-3
 
 _REPORT = []
 
@@ -80,7 +82,7 @@ def _run(model, step, amp, extras=None):
     outs = [o.detach().float() for o in outs]
     if extras is not None:          # tensors only available after backward (input gradients)
         outs += [e.detach().float().clone() for e in extras()]
-    return outs, float(loss), _grads(model)
+    return outs, float(loss.detach()), _grads(model)
 
 
 def _compare(name, ref_model, our_model, step, out_names, extras=None):

@@ -23,8 +23,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "vit-is-all-you-need_b200")
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not loader.available(), reason="baseline/_ref (reference copy) not present")]
 
-FIRST_TOL = 2e-2     # first logged loss (no optimizer step in between, or one): relative
-TRAJ_TOL = 6e-2      # every later logged loss: relative (fp16-autocast eager vs bf16 kernels drift apart slowly)
+# measured on a B200 (profiles/r2_script_trajectories.json): the two trajectories agree to 1e-4 .. 3e-4 relative at every step
+FIRST_TOL = 5e-3     # first logged loss (no optimizer step in between, or one): relative
+TRAJ_TOL = 2e-2      # every later logged loss: relative (fp16-autocast eager vs bf16 kernels drift apart slowly)
 
 
 def _run(script, args, workdir, plain, samples, extra_env=None):

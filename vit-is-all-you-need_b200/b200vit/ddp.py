@@ -15,7 +15,10 @@ Mechanics
     all-reduce is enqueued on a communication stream;
   * an autograd end-of-backward callback waits for all buckets and points `param.grad` at the (averaged)
     bucket views, so optimisers / GradScaler / clip_grad_norm_ run unchanged.
-Gradient accumulation over several backward passes is only supported inside `no_sync()`.
+Gradient accumulation: micro-steps run inside `no_sync()` (gradients accumulate in `param.grad` through autograd, nothing is
+reduced); on the following synchronised step every parameter whose `.grad` already holds something is NOT offered a bucket
+slot (`grad_slot` -> None), so its new gradient is ADDED to the accumulated one by autograd and the post-accumulate hook
+copies the sum into the bucket -- fused and hook-delivered parameters reduce the same quantity.
 """
 import contextlib
 
@@ -74,13 +77,20 @@ class DataParallel(torch.nn.Module):
 
     # ---------------------------------------------------------------------------------------------- plumbing
     def broadcast_parameters(self):
+        """Rank 0's parameters / buffers to every rank.  Writes through `.data` do not bump Tensor._version, so the cached
+        bf16 GEMM operands of the parameters are dropped explicitly (call this again after loading a checkpoint on rank 0)."""
         if self.world > 1:
             for t in list(self.module.parameters()) + list(self.module.buffers()):
                 dist.broadcast(t.data, src=0, group=self.pg)
+        Fn.invalidate_weight_cache(self.module)
 
     def forward(self, *args, **kwargs):
         # the fused autograd nodes created during this forward capture the sink; other models in the process
         # (a second wrapper, an un-wrapped teacher ...) are unaffected
+        if self._in_backward and torch.is_grad_enabled():
+            # a backward that raised never reached _finalize (the engine drops its callbacks): without this reset no later
+            # backward would re-arm the buckets and the ranks would silently diverge
+            self._reset_backward_state()
         prev = Fn.set_grad_sink(self if (self._sync and torch.is_grad_enabled()) else None)
         try:
             return self.module(*args, **kwargs)
@@ -97,9 +107,17 @@ class DataParallel(torch.nn.Module):
 
     # ---------------------------------------------------------------------------------- gradient sink protocol
     def grad_slot(self, param):
-        """Bucket view the producer may write this parameter's gradient into (None if unknown)."""
+        """Bucket view the producer may OVERWRITE with this parameter's gradient, or None when the gradient has to go
+        through autograd: unknown parameter; `.grad` already populated (accumulation after no_sync() micro-steps, or a
+        caller that did not zero the gradients); or the parameter was already delivered in this backward (weight sharing /
+        a wrapped stack that ran twice in one forward -- its bucket may be in flight)."""
         s = self._slots.get(param)
-        return None if s is None else s[1]
+        if s is None or not self._sync or param.grad is not None:
+            return None
+        b, view = s
+        if self._in_backward and param in b.ready:
+            return None
+        return view
 
     def grad_ready(self, param):
         if param in self._slots:
@@ -110,10 +128,25 @@ class DataParallel(torch.nn.Module):
             return
         b, view = self._slots[param]
         if self._in_backward and param in b.ready:
-            return  # already delivered through the gradient sink (the bucket may be in flight)
+            if param.grad is None or param.grad.data_ptr() == view.data_ptr():
+                return  # delivered through the gradient sink: torch fires this hook even for the None autograd received
+            # a second gradient for a parameter whose bucket slot has been handed over already (the all-reduce may be in
+            # flight): it cannot be folded in any more -- fail instead of training on a partial gradient
+            raise RuntimeError("b200vit.ddp.DataParallel: a parameter received a second gradient in the same backward after "
+                               "its all-reduce bucket was released (shared weights / a fused stack used twice in one forward "
+                               "are not supported under DataParallel)")
         if param.grad is not None and param.grad.data_ptr() != view.data_ptr():
             view.copy_(param.grad)
         self._mark_ready(param)
+
+    def _reset_backward_state(self):
+        self._in_backward = False
+        for b in self.buckets:
+            if b.work is not None:
+                b.work.wait()
+            b.pending = len(b.params)
+            b.work = None
+            b.ready = set()
 
     def _begin_backward(self):
         self._in_backward = True

@@ -58,6 +58,20 @@ def bf16_of(p: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def invalidate_weight_cache(module_or_params=None):
+    """Drops the cached bf16 GEMM operands.  Needed after parameter writes that neither bump Tensor._version nor go through
+    an optimizer step: `p.data.copy_(...)`, `dist.broadcast(p.data)`, EMA updates through `.data`.  With no argument every
+    cache in the process is invalidated (the epoch in the cache key advances)."""
+    global _WEIGHT_EPOCH
+    if module_or_params is None:
+        _WEIGHT_EPOCH += 1
+        return
+    params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
+    for p in params:
+        if hasattr(p, "_b200_bf16"):
+            del p._b200_bf16
+
+
 # ------------------------------------------------------------------------------------------------------------
 # Gradient sink (set by ddp.DataParallel): lets the wgrad kernels write straight into all-reduce buckets and
 # start a bucket's all-reduce while the rest of the fused backward is still running.
@@ -150,30 +164,36 @@ def layer_backward(dx2, dx2_bf16, saved, P: LayerParams, B, N, H, causal, need_d
     """dx2: [B*N, d] fp32 (dx2_bf16: optional bf16 copy).  Returns (dx0, dx0_bf16, grads in LayerParams order)."""
     rstd1, a, qkv, o, lse, rstd2, b, u, g, seeds = saved
     p_attn, p_mlp = dropout
+    # all-reduce bucket slots, asked for ONCE per parameter: the sink answers None when the gradient has to go through
+    # autograd instead (no sink; p.grad already holds micro-batch gradients from no_sync() steps; parameter delivered before)
+    params = (P.qkv_w, P.qkv_b, P.fc1_w, P.fc1_b, P.fc2_w, P.fc2_b)
+    s_qkv_w, s_qkv_b, s_fc1_w, s_fc1_b, s_fc2_w, s_fc2_b = slots = tuple(_slot(sink, q) for q in params)
+
+    def delivered(*pairs):      # gradients that were written straight into their slots are complete: start their bucket
+        _ready(sink, *(q for q, s_ in pairs if s_ is not None))
+
     if p_mlp > 0.0:
         dv = ops.dropout_cast_bf16(dx2, p_mlp, seeds[1])   # gradient through nn.Dropout, same mask as forward
     else:
         dv = dx2_bf16 if dx2_bf16 is not None else ops.cast_bf16(dx2)
-    d_fc2_w, d_fc2_b = ops.gemm_wgrad(dv, g, out=_slot(sink, P.fc2_w), bias_out=_slot(sink, P.fc2_b), want_bias=True)
-    _ready(sink, P.fc2_w, P.fc2_b)
+    d_fc2_w, d_fc2_b = ops.gemm_wgrad(dv, g, out=s_fc2_w, bias_out=s_fc2_b, want_bias=True)
+    delivered((P.fc2_w, s_fc2_w), (P.fc2_b, s_fc2_b))
     du = ops.gemm_dgrad_dgelu(dv, bf16_of(P.fc2_w), u)
-    d_fc1_w, d_fc1_b = ops.gemm_wgrad(du, b, out=_slot(sink, P.fc1_w), bias_out=_slot(sink, P.fc1_b), want_bias=True)
-    _ready(sink, P.fc1_w, P.fc1_b)
+    d_fc1_w, d_fc1_b = ops.gemm_wgrad(du, b, out=s_fc1_w, bias_out=s_fc1_b, want_bias=True)
+    delivered((P.fc1_w, s_fc1_w), (P.fc1_b, s_fc1_b))
     db = ops.gemm_dgrad(du, bf16_of(P.fc1_w))
     dx1, dx1_bf16 = ops.layernorm_bwd_xhat(db, b, rstd2, dres=dx2, want_bf16=True)
     dqkv = ops.flash_attn_bwd(qkv, o, dx1_bf16.view(B, N, -1), lse, B, N, H, causal, dropout_p=p_attn, seed=seeds[0]).view(B * N, -1)
-    d_qkv_w, d_qkv_b = ops.gemm_wgrad(dqkv, a, out=_slot(sink, P.qkv_w), bias_out=_slot(sink, P.qkv_b), want_bias=True)
-    _ready(sink, P.qkv_w, P.qkv_b)
+    d_qkv_w, d_qkv_b = ops.gemm_wgrad(dqkv, a, out=s_qkv_w, bias_out=s_qkv_b, want_bias=True)
+    delivered((P.qkv_w, s_qkv_w), (P.qkv_b, s_qkv_b))
     dx0 = dx0_bf16 = None
     if need_dx:
         da = ops.gemm_dgrad(dqkv, bf16_of(P.qkv_w))
         dx0, dx0_bf16 = ops.layernorm_bwd_xhat(da, a, rstd1, dres=dx1, want_bf16=True)
     grads = (d_qkv_w, d_qkv_b, d_fc1_w, d_fc1_b, d_fc2_w, d_fc2_b)
-    if sink is not None:
-        # gradients already sit in their all-reduce bucket slots and have been marked ready: hand autograd None so
-        # that AccumulateGrad does not clone them into a second buffer (the sink points param.grad at the slots)
-        params = (P.qkv_w, P.qkv_b, P.fc1_w, P.fc1_b, P.fc2_w, P.fc2_b)
-        grads = tuple(None if _slot(sink, q) is not None else g_ for q, g_ in zip(params, grads))
+    # gradients that already sit in their bucket slots have been marked ready: hand autograd None for those so that
+    # AccumulateGrad does not clone them into a second buffer (the sink points param.grad at the slots)
+    grads = tuple(None if s_ is not None else g_ for s_, g_ in zip(slots, grads))
     return dx0, dx0_bf16, grads
 
 

@@ -21,6 +21,10 @@ class GraphedTrainStep:
         for m in model.modules():
             if float(getattr(m, "dropout", 0.0) or 0.0) > 0.0 and hasattr(m, "n_embd"):
                 raise ValueError("GraphedTrainStep: dropout > 0 would replay the captured masks; use eager steps")
+        for group in optimizer.param_groups:
+            if not group.get("capturable", False):
+                raise ValueError("GraphedTrainStep: the optimizer must be built with capturable=True (a host-side step counter "
+                                 "would be frozen into the graph)")
         self.model, self.optimizer, self.loss_fn = model, optimizer, loss_fn
         self.autocast_dtype = autocast_dtype
         self.static_x = example_inputs.clone()

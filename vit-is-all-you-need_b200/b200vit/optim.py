@@ -98,6 +98,13 @@ class AdamW(torch.optim.Optimizer):
                 loss = closure()
         grad_scale = getattr(self, "grad_scale", None)   # set by GradScaler.step around this call
         found_inf = getattr(self, "found_inf", None)
+        if torch.cuda.is_current_stream_capturing():
+            # like torch's _cuda_graph_capture_health_check: a host-side step count / bias correction captured into a graph
+            # would be replayed unchanged for ever (state["step"] never advances, every replay applies step-1 corrections)
+            for group in self.param_groups:
+                if not group["capturable"] and found_inf is None and any(p.grad is not None for p in group["params"]):
+                    raise RuntimeError("b200vit.optim.AdamW: capturing step() in a CUDA graph needs capturable=True (the step "
+                                       "counter and bias corrections must live on the device)")
         for gi, group in enumerate(self.param_groups):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:
@@ -179,6 +186,14 @@ class AdamW(torch.optim.Optimizer):
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._tables = {}
+        # Optimizer.load_state_dict moves `step` to the parameter's device because defaults say fused=True; the host-step
+        # path would then pay one .item() sync per parameter and step: keep host counters on the host
+        for group in self.param_groups:
+            if not group["capturable"]:
+                for p in group["params"]:
+                    st = self.state.get(p)
+                    if st and isinstance(st.get("step"), torch.Tensor) and st["step"].device.type != "cpu":
+                        st["step"] = st["step"].detach().to("cpu", torch.float32)
 
 
 __all__ = ["AdamW"]

@@ -105,10 +105,14 @@ ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict
                  int C, long long ignore_index) {
   __shared__ float ssum[8];
   __shared__ float scnt[8];
+  // a label outside [0, C) that is not ignore_index is an error (torch: device assert).  There is no host sync here, so
+  // the loud equivalent is a NaN loss and, through loss[1], NaN gradients: a label / vocabulary mismatch cannot train silently
   float s = 0.f, n = 0.f;
   for (int r = threadIdx.x; r < R; r += 256) {
     const long long y = labels[r];
-    if (!(y == ignore_index || y < 0 || y >= C)) { s += row_loss[r]; n += 1.f; }
+    if (y == ignore_index) continue;
+    if (y < 0 || y >= C) { s = nanf(""); n += 1.f; continue; }
+    s += row_loss[r]; n += 1.f;
   }
   s = warp_sum(s); n = warp_sum(n);
   if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; scnt[threadIdx.x >> 5] = n; }
@@ -117,7 +121,7 @@ ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict
     float ts = 0.f, tn = 0.f;
     for (int i = 0; i < 8; ++i) { ts += ssum[i]; tn += scnt[i]; }
     loss[0] = tn > 0.f ? ts / tn : nanf("");   // torch: mean over zero rows is nan
-    loss[1] = tn > 0.f ? 1.f / tn : 0.f;
+    loss[1] = tn > 0.f ? (ts != ts ? ts : 1.f / tn) : 0.f;
   }
 }
 
@@ -221,9 +225,11 @@ embed_fwd_kernel(const long long* __restrict__ idx, const float* __restrict__ to
     const long long r = i / per_row;
     const int c = (int)(i - r * per_row) * 4;
     long long t = idx[r];
-    t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);   // host validates; never read out of bounds
+    const bool bad = t < 0 || t >= vocab;          // torch's embedding raises a device assert; without a host sync the
+    t = bad ? 0 : t;                               // loud equivalent is a NaN row (never read out of bounds)
     const int s = (int)(r % S);
-    const float4 a = __ldg(reinterpret_cast<const float4*>(tok + t * d + c));
+    float4 a = __ldg(reinterpret_cast<const float4*>(tok + t * d + c));
+    if (bad) a.x = a.y = a.z = a.w = nanf("");
     const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (long long)(pos0 + s) * d + c));
     *reinterpret_cast<float4*>(out + r * d + c) = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
   }
