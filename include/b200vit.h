@@ -120,6 +120,35 @@ int b200vit_patch_embed_fwd(const float* x, const void* w_bf16, const float* bia
 /* dsum[T, d] = sum_b dtokens[b] ; dpe_bf16[B*P, d] = bf16(dtokens[:, extra:])                                */
 int b200vit_patch_embed_bwd_reduce(const float* dtokens, float* dsum, void* dpe_bf16, int B, int T, int extra,
                                    int d, void* stream);
+/* Token-sequence assembly of blocks.TiTokEncoder / TiTokDecoder (blocks.py:254-268, 337-352): ONE GEMM over bf16 operand
+ * rows (im2col of the image for the encoder's patch_embed blocks.py:235,257; the latent rows for the decoder's
+ * decoder_embed blocks.py:310,341) whose epilogue adds bias + pos and writes rows [extra, extra+P) of tokens[B, T, d]
+ * (T = extra + P + tail, fp32), plus one pass that fills the rows no GEMM produces:
+ *   head rows e < extra : (e == 0 ? head0 : head1)[d] + head_pos[e, d]  (class_embedding / mask_token + positional_embedding)
+ *   tail rows l < tail  : tail_a[l, d] + tail_b[l, d]                   (latent_tokens + latent_token_positional_embedding)
+ * i.e. torch.cat / expand / the two position adds of blocks.py:261-267 never run as separate passes.              */
+int b200vit_tokens_assemble_fwd(const void* cols_bf16, const void* w_bf16, const float* bias, const float* pos,
+                                const float* head0, const float* head1, const float* head_pos, const float* tail_a,
+                                const float* tail_b, float* tokens, int B, int P, int K, int d, int extra, int tail,
+                                void* stream);
+/* dsum[T, d] = sum_b dtokens[b] (gradients of every broadcast row and positional table) ;
+ * dpe_bf16[B*P, d] = bf16(dtokens[:, extra:extra+P]) (operand of the wgrad / dgrad GEMMs)                          */
+int b200vit_tokens_assemble_bwd_reduce(const float* dtokens, float* dsum, void* dpe_bf16, int B, int T, int extra, int tail,
+                                       int d, void* stream);
+/* out[B, cnt, d] (f32) = x[:, t0:t0+cnt, :] -- the ln_post input of blocks.py:276,359                               */
+int b200vit_gather_tokens_f32(const float* x, float* out, int B, int N, int d, int t0, int cnt, void* stream);
+/* Affine LayerNorm folded into the Linear that follows it (blocks.py:66 ln_1 -> attn.in_proj, blocks.py:69 ln_2 -> mlp.c_fc):
+ * Linear(gamma*xhat + beta) = xhat (W diag(gamma))^T + (b + W beta), so blocks.ResidualAttentionBlock runs on the
+ * affine-free LayerNorm / GEMM kernels of transformer.TransformerLayer and keeps only the bf16 xhat for backward.
+ *   fold  : W_bf16[N,K] = bf16(W * gamma) ; bias_out[N] = bias (may be NULL) + W beta
+ *   unfold: dW[n,k] = dW'[n,k] gamma[k] + dbias[n] beta[k] (in place; dW' = the wgrad result on xhat, dbias = its bias
+ *           gradient) ; dgamma[K] (+)= sum_n dW'[n,k] W[n,k] ; dbeta[K] (+)= sum_n W[n,k] dbias[n]   (fixed summation order) */
+int b200vit_affine_fold(const float* W, const float* bias, const float* gamma, const float* beta, void* W_bf16,
+                        float* bias_out, int N, int K, void* stream);
+size_t b200vit_affine_unfold_workspace_size(int K);
+int b200vit_affine_unfold_grads(float* dW, const float* W, const float* gamma, const float* beta, const float* dbias,
+                                float* dgamma, float* dbeta, int N, int K, int accumulate, void* workspace,
+                                size_t workspace_bytes, void* stream);
 /* de-patchify tail of the tokenizer decoders (train_titok.py:67,72-74): 1x1 Conv2d(d -> C*p*p) over the patch tokens +
  * "b (p1 p2 c) h w -> b c (h p1) (w p2)" as ONE GEMM whose epilogue stores straight into the NCHW image.
  * rows_bf16[B*P, d]; w_cmajor_bf16[C*p*p, d] and bias_cmajor[C*p*p] hold the conv's output channels re-ordered from the

@@ -263,3 +263,87 @@ def test_transformer_stack_standalone_and_attention_module():
             return [y], (y.float() * w).mean()
         _compare(f"transformer.Attention (qkv + SDPA, no out-proj), causal={causal}, N={N}", ref_att, our_att, att_step,
                  ["attention output", "d x"], extras=lambda: [xa.grad])
+
+
+class _BlocksCfg:     # the attributes blocks.TiTokEncoder / TiTokDecoder read from their config (blocks.py:211-217)
+    def __init__(self, image_size=256, patch_size=16, transformer="small", latent_tokens=32, latent_dim=12):
+        self.image_size, self.patch_size, self.transformer = image_size, patch_size, transformer
+        self.latent_tokens, self.latent_dim = latent_tokens, latent_dim
+
+
+@pytest.mark.parametrize("mlp_ratio", [4.0, 0])
+def test_residual_attention_block_full_size(mlp_ratio):
+    """blocks.ResidualAttentionBlock (blocks.py:32-70) on its own in the reference's LND layout: d 512, 8 heads, L = 289
+    (1 + 256 + 32, config 3'), batch 8; mlp_ratio = 0 disables the FFN (blocks.py:47,68)."""
+    from b200vit import modules as M
+    ref = loader.load()
+    ref_blk, our_blk = _pair(lambda: ref.blocks.ResidualAttentionBlock(512, 8, mlp_ratio=mlp_ratio),
+                             lambda: M.ResidualAttentionBlock(512, 8, mlp_ratio=mlp_ratio))
+    with torch.no_grad():       # LayerNorm parameters away from their (1, 0) init so that the folded path is exercised
+        for m in (ref_blk, our_blk):
+            g = torch.Generator().manual_seed(11)
+            for name, p in m.named_parameters():
+                if name.startswith("ln_"):
+                    p.add_(0.3 * torch.randn(p.shape, generator=g).to(DEV))
+    x = torch.randn(289, 8, 512, generator=torch.Generator().manual_seed(12)).to(DEV).requires_grad_(True)
+    w = torch.randn(289, 8, 512, generator=torch.Generator().manual_seed(13)).to(DEV)
+
+    def step(model):
+        x.grad = None
+        y = model(x)
+        return [y], (y.float() * w).mean()
+    _compare(f"blocks.ResidualAttentionBlock [L=289, B=8, 512], mlp_ratio={mlp_ratio}", ref_blk, our_blk, step, ["y", "d x"],
+             extras=lambda: [x.grad])
+
+
+def _perturb_layernorms(ref_model, our_model, seed):
+    with torch.no_grad():
+        for m in (ref_model, our_model):
+            g = torch.Generator().manual_seed(seed)
+            for name, p in m.named_parameters():
+                if ".ln_" in name or name.startswith("ln_"):
+                    p.add_(0.2 * torch.randn(p.shape, generator=g).to(DEV))
+
+
+def test_blocks_titok_encoder_decoder_small_256():
+    """blocks.TiTokEncoder / TiTokDecoder (blocks.py:208-361; config 3': small, 256 px, patch 16, 32 latent tokens of dim 12,
+    N = 1 + 256 + 32 = 289) against the reference's own classes: the fused token-sequence assembly (patch embedding, class
+    token, both positional tables, latent / mask tokens), ln_pre, 8 ResidualAttentionBlocks, ln_post, conv_out / ffn."""
+    from b200vit import modules as M
+    ref = loader.load()
+    cfg = _BlocksCfg()
+    B = 16
+    ref_enc, our_enc = _pair(lambda: ref.blocks.TiTokEncoder(cfg), lambda: M.BlocksTiTokEncoder(cfg))
+    _perturb_layernorms(ref_enc, our_enc, 21)
+    x = torch.rand(B, 3, 256, 256, generator=torch.Generator().manual_seed(22)).to(DEV)
+    latent = (512 ** -0.5 * torch.randn(32, 512, generator=torch.Generator().manual_seed(23))).to(DEV).requires_grad_(True)
+    w = torch.randn(B, 12, 1, 32, generator=torch.Generator().manual_seed(24)).to(DEV)
+
+    def enc_step(model):
+        latent.grad = None
+        z = model(x, latent)
+        return [z], (z.float() * w).mean()
+    _compare("blocks.TiTokEncoder small 256px, batch 16", ref_enc, our_enc, enc_step, ["latents [B,12,1,32]", "d latent_tokens"],
+             extras=lambda: [latent.grad])
+
+    ref_dec, our_dec = _pair(lambda: ref.blocks.TiTokDecoder(cfg), lambda: M.BlocksTiTokDecoder(cfg))
+    _perturb_layernorms(ref_dec, our_dec, 25)
+    zq = torch.nn.functional.normalize(torch.randn(B, 12, 1, 32, generator=torch.Generator().manual_seed(26)), dim=1).to(DEV).requires_grad_(True)
+
+    def dec_step(model):
+        zq.grad = None
+        img = model(zq)
+        return [img], (img.float() - x).square().mean()
+    _compare("blocks.TiTokDecoder small 256px, batch 16", ref_dec, our_dec, dec_step, ["image", "d z_quantized"], extras=lambda: [zq.grad])
+
+    # encoder -> VectorQuantizer -> decoder chained, as train_tatitok.TiTok does (train_tatitok.py:40-41,62-75): indices bit-exact
+    # on identical fp32 latents
+    ref_vq = ref.blocks.VectorQuantizer(4096, 12, 0.25, use_l2_norm=True).to(DEV)
+    our_vq = M.VectorQuantizer(4096, 12, 0.25, use_l2_norm=True).to(DEV)
+    our_vq.load_state_dict(ref_vq.state_dict())
+    with torch.no_grad(), _NoTF32():
+        z = ref_enc(x, latent).float()
+        zq_r, info_r = ref_vq(z)
+        zq_o, info_o = our_vq(z)
+    assert torch.equal(info_o["min_encoding_indices"], info_r["min_encoding_indices"])
+    assert float((zq_o - zq_r).abs().max()) <= 5e-7

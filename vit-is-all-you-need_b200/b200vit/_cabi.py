@@ -66,6 +66,12 @@ _SIGNATURES = {
     "b200vit_cast_f32_bf16": (_I, [_P, _P, _L, _P]),
     "b200vit_patch_embed_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200vit_patch_embed_bwd_reduce": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200vit_tokens_assemble_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200vit_tokens_assemble_bwd_reduce": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200vit_gather_tokens_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200vit_affine_fold": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "b200vit_affine_unfold_workspace_size": (_Z, [_I]),
+    "b200vit_affine_unfold_grads": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _Z, _P]),
     "b200vit_im2col_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "b200vit_col2im_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "b200vit_gather_tokens_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

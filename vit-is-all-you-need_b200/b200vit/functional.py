@@ -21,10 +21,12 @@ F32 = torch.float32
 # epoch that is part of the cache key: after ANY optimizer step every cached operand is re-cast on next use.
 # b200vit.optim.AdamW writes the refreshed bf16 operands itself and is exempt (it re-keys the caches it has updated).
 _WEIGHT_EPOCH = 0
+_STEP_EPOCH = 0     # advances on EVERY optimizer step: key of the LayerNorm-folded operands (folded_of), which no optimizer refreshes
 
 
 def _optimizer_stepped(optimizer, *_args, **_kwargs):
-    global _WEIGHT_EPOCH
+    global _WEIGHT_EPOCH, _STEP_EPOCH
+    _STEP_EPOCH += 1
     if not getattr(optimizer, "_b200_refreshes_bf16", False):
         _WEIGHT_EPOCH += 1
 
@@ -62,14 +64,33 @@ def invalidate_weight_cache(module_or_params=None):
     """Drops the cached bf16 GEMM operands.  Needed after parameter writes that neither bump Tensor._version nor go through
     an optimizer step: `p.data.copy_(...)`, `dist.broadcast(p.data)`, EMA updates through `.data`.  With no argument every
     cache in the process is invalidated (the epoch in the cache key advances)."""
-    global _WEIGHT_EPOCH
+    global _WEIGHT_EPOCH, _STEP_EPOCH
     if module_or_params is None:
         _WEIGHT_EPOCH += 1
+        _STEP_EPOCH += 1
         return
     params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
     for p in params:
-        if hasattr(p, "_b200_bf16"):
-            del p._b200_bf16
+        for attr in ("_b200_bf16", "_b200_folded"):
+            if hasattr(p, attr):
+                delattr(p, attr)
+
+
+def folded_of(W, bias, gamma, beta):
+    """(bf16(W diag(gamma)), bias + W beta): the operands of a Linear with the affine LayerNorm in front of it folded in
+    (csrc/affine_fold.cu), cached on W until any of the four parameters changes or an optimizer steps."""
+    key = (_STEP_EPOCH, W._version, W.data_ptr(), gamma._version, gamma.data_ptr(), beta._version, beta.data_ptr(),
+           None if bias is None else (bias._version, bias.data_ptr()))
+    cached = getattr(W, "_b200_folded", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    out = cached[1] if (cached is not None and not torch.cuda.is_current_stream_capturing()) else None   # refresh in place
+    out = ops.affine_fold(_f32c(W), _f32c(bias), _f32c(gamma), _f32c(beta), out=out)
+    try:
+        W._b200_folded = (key, out)
+    except Exception:  # pragma: no cover
+        pass
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -558,66 +579,232 @@ class CrossEntropyFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------------
 # blocks.ResidualAttentionBlock (blocks.py:32-70): affine LN, MHA (in_proj + out_proj), [L, B, d] layout
 # blocks.UViTBlock (blocks.py:174-201): the same block batch-first ([B, L, d]), QKV bias optional
+#
+# The two affine LayerNorms are folded into the Linear that follows each (in_proj, c_fc): see folded_of / csrc/affine_fold.cu.
+# The block then runs on the affine-free LayerNorm + GEMM kernels of transformer.TransformerLayer, keeps only the bf16 x-hat
+# (no fp32 residual rows, no means) for backward, and a stack of blocks is ONE autograd node that hands the bf16 twin of
+# the residual gradient from layer to layer and delivers its weight gradients into the data-parallel buckets.
 # ------------------------------------------------------------------------------------------------------------
-class ResidualAttentionBlockFn(torch.autograd.Function):
+class RABParams:
+    __slots__ = ("ln1_w", "ln1_b", "in_w", "in_b", "out_w", "out_b", "ln2_w", "ln2_b", "fc_w", "fc_b", "proj_w", "proj_b")
+    N_ATTN, N_ALL = 6, 12
+
+    def __init__(self, *p):
+        p = tuple(p) + (None,) * (self.N_ALL - len(p))
+        (self.ln1_w, self.ln1_b, self.in_w, self.in_b, self.out_w, self.out_b,
+         self.ln2_w, self.ln2_b, self.fc_w, self.fc_b, self.proj_w, self.proj_b) = p
+
+    def tensors(self, has_mlp):
+        t = (self.ln1_w, self.ln1_b, self.in_w, self.in_b, self.out_w, self.out_b)
+        return t + ((self.ln2_w, self.ln2_b, self.fc_w, self.fc_b, self.proj_w, self.proj_b) if has_mlp else ())
+
+
+def rab_layer_forward(x0, P: RABParams, B, L, H, seq_first, has_mlp, save):
+    """x0 [rows, d] fp32 (rows ordered (b, l), or (l, b) when seq_first).  Returns (x_out fp32, saved)."""
+    M, d = x0.shape
+    xh1, _, _, rstd1, _ = ops.layernorm_fwd(x0)                               # affine-free x-hat; gamma / beta live in w_in / b_in
+    w_in, b_in = folded_of(P.in_w, P.in_b, P.ln1_w, P.ln1_b)
+    qkv = ops.gemm_bias(xh1, w_in, b_in)
+    o, lse = ops.flash_attn_fwd(qkv, B, L, H, False, want_lse=save, seq_first=seq_first)
+    o2 = o.view(M, d)
+    x1 = ops.gemm_bias_residual(o2, bf16_of(P.out_w), _f32c(P.out_b), x0)     # out_proj + residual (blocks.py:60,67)
+    if not has_mlp:
+        return x1, ((rstd1, xh1, qkv, o, lse) if save else None)
+    xh2, _, _, rstd2, _ = ops.layernorm_fwd(x1)
+    w_fc, b_fc = folded_of(P.fc_w, P.fc_b, P.ln2_w, P.ln2_b)
+    g, u = ops.gemm_bias_gelu(xh2, w_fc, b_fc)                                # u := GELU'(pre-activation)
+    x2 = ops.gemm_bias_residual(g, bf16_of(P.proj_w), _f32c(P.proj_b), x1)
+    return x2, ((rstd1, xh1, qkv, o, lse, rstd2, xh2, u, g) if save else None)
+
+
+def _folded_linear_backward(dy16, xhat, W, bias, gamma, beta, sink):
+    """Gradients of Linear(affine LN(.)) with the LN folded into the weights: wgrad on x-hat -> dW', db'; then
+    dW = dW' diag(gamma) + db' (x) beta, dgamma = colsum(dW' * W), dbeta = W^T db' (affine_unfold_grads).  Returns the four gradients in
+    the order (gamma, beta, W, bias); entries that were written into their data-parallel bucket slots come back as None."""
+    s_w, s_b, s_g, s_be = _slot(sink, W), (_slot(sink, bias) if bias is not None else None), _slot(sink, gamma), _slot(sink, beta)
+    dW, db = ops.gemm_wgrad(dy16, xhat, out=s_w, bias_out=s_b, want_bias=True)
+    dg, dbe = ops.affine_unfold_grads(dW, _f32c(W), _f32c(gamma), _f32c(beta), db, dgamma=s_g if s_be is not None else None,
+                                      dbeta=s_be if s_g is not None else None)
+    both = s_g is not None and s_be is not None     # the pair goes through the sink together or not at all
+    _ready(sink, *(q for q, s_ in ((W, s_w), (bias, s_b), (gamma, s_g if both else None), (beta, s_be if both else None)) if s_ is not None))
+    return (None if both else dg, None if both else dbe, None if s_w is not None else dW,
+            None if (s_b is not None or bias is None) else db)
+
+
+def rab_layer_backward(dx2, dx2_bf16, saved, P: RABParams, B, L, H, seq_first, has_mlp, need_dx, sink):
+    """Returns (dx0 fp32, dx0 bf16, gradients in RABParams.tensors(has_mlp) order)."""
+    M, d = dx2.shape
+    mlp_grads = ()
+    if has_mlp:
+        rstd1, xh1, qkv, o, lse, rstd2, xh2, u, g = saved
+        dv = dx2_bf16 if dx2_bf16 is not None else ops.cast_bf16(dx2)
+        s_pw, s_pb = _slot(sink, P.proj_w), _slot(sink, P.proj_b)
+        d_proj_w, d_proj_b = ops.gemm_wgrad(dv, g, out=s_pw, bias_out=s_pb, want_bias=True)
+        _ready(sink, *(q for q, s_ in ((P.proj_w, s_pw), (P.proj_b, s_pb)) if s_ is not None))
+        du = ops.gemm_dgrad_dgelu(dv, bf16_of(P.proj_w), u)
+        d_ln2_w, d_ln2_b, d_fc_w, d_fc_b = _folded_linear_backward(du, xh2, P.fc_w, P.fc_b, P.ln2_w, P.ln2_b, sink)
+        db = ops.gemm_dgrad(du, folded_of(P.fc_w, P.fc_b, P.ln2_w, P.ln2_b)[0])
+        dx1, dx1_16 = ops.layernorm_bwd_xhat(db, xh2, rstd2, dres=dx2, want_bf16=True)
+        mlp_grads = (d_ln2_w, d_ln2_b, d_fc_w, d_fc_b, None if s_pw is not None else d_proj_w, None if s_pb is not None else d_proj_b)
+    else:
+        rstd1, xh1, qkv, o, lse = saved
+        dx1, dx1_16 = dx2, (dx2_bf16 if dx2_bf16 is not None else ops.cast_bf16(dx2))
+    s_ow, s_ob = _slot(sink, P.out_w), _slot(sink, P.out_b)
+    d_out_w, d_out_b = ops.gemm_wgrad(dx1_16, o.view(M, d), out=s_ow, bias_out=s_ob, want_bias=True)
+    _ready(sink, *(q for q, s_ in ((P.out_w, s_ow), (P.out_b, s_ob)) if s_ is not None))
+    do = ops.gemm_dgrad(dx1_16, bf16_of(P.out_w))
+    dqkv = ops.flash_attn_bwd(qkv, o, do.view(o.shape), lse, B, L, H, False, seq_first=seq_first).view(M, -1)
+    d_ln1_w, d_ln1_b, d_in_w, d_in_b = _folded_linear_backward(dqkv, xh1, P.in_w, P.in_b, P.ln1_w, P.ln1_b, sink)
+    dx0 = dx0_16 = None
+    if need_dx:
+        da = ops.gemm_dgrad(dqkv, folded_of(P.in_w, P.in_b, P.ln1_w, P.ln1_b)[0])
+        dx0, dx0_16 = ops.layernorm_bwd_xhat(da, xh1, rstd1, dres=dx1, want_bf16=True)
+    grads = (d_ln1_w, d_ln1_b, d_in_w, d_in_b, None if s_ow is not None else d_out_w, None if s_ob is not None else d_out_b) + mlp_grads
+    return dx0, dx0_16, grads
+
+
+class ResidualAttentionStackFn(torch.autograd.Function):
+    """n x blocks.ResidualAttentionBlock (n = 1: the module on its own; n = num_layers: the transformer of
+    blocks.TiTokEncoder / TiTokDecoder, blocks.py:246-251,271-272) as one autograd node.  x is [L, B, d] (the reference's
+    LND layout) or, with batch_first, [B, L, d] (UViTBlock; the internal layout of the encoder / decoder drop-ins)."""
+
     @staticmethod
-    def forward(ctx, x, n_heads, has_mlp, batch_first, ln1_w, ln1_b, in_w, in_b, out_w, out_b, *mlp):
+    def forward(ctx, x, n_heads, has_mlp, batch_first, *params):
         if batch_first:
             B, L, d = x.shape
         else:
             L, B, d = x.shape
-        M = L * B
-        x0 = _as_rows_f32(x).view(M, d)
-        a, _, mean1, rstd1, _ = ops.layernorm_fwd(x0, gamma=_f32c(ln1_w), beta=_f32c(ln1_b))
-        qkv = ops.gemm_bias(a, bf16_of(in_w), _f32c(in_b))
-        o, lse = ops.flash_attn_fwd(qkv, B, L, n_heads, False, seq_first=not batch_first)
-        o2 = o.view(M, d)
-        x1 = ops.gemm_bias_residual(o2, bf16_of(out_w), _f32c(out_b), x0)
-        saved = [x0, mean1, rstd1, a, qkv, o, lse, x1]
-        y = x1
-        if has_mlp:
-            ln2_w, ln2_b, fc_w, fc_b, proj_w, proj_b = mlp
-            b, _, mean2, rstd2, _ = ops.layernorm_fwd(x1, gamma=_f32c(ln2_w), beta=_f32c(ln2_b))
-            g, u = ops.gemm_bias_gelu(b, bf16_of(fc_w), _f32c(fc_b))
-            y = ops.gemm_bias_residual(g, bf16_of(proj_w), _f32c(proj_b), x1)
-            saved += [mean2, rstd2, b, u, g]
-        ctx.saved = saved
-        ctx.params = (ln1_w, in_w, out_w) + tuple(mlp)
-        ctx.dims = (L, B, d, n_heads, has_mlp, batch_first, tuple(x.shape), in_b is not None)
-        return y.view(x.shape)
+        per = RABParams.N_ALL if has_mlp else RABParams.N_ATTN
+        layers = [RABParams(*params[per * i:per * (i + 1)]) for i in range(len(params) // per)]
+        need_grad = any(ctx.needs_input_grad)
+        h = _as_rows_f32(x).view(L * B, d)
+        saved_all = []
+        for P in layers:
+            h, saved = rab_layer_forward(h, P, B, L, n_heads, not batch_first, has_mlp, need_grad)
+            saved_all.append(saved)
+        ctx.layers, ctx.saved_all = layers, saved_all
+        ctx.dims = (B, L, d, n_heads, has_mlp, batch_first, tuple(x.shape))
+        ctx.sink = _GRAD_SINK
+        ctx.x_needs_grad = x.requires_grad
+        return h.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
-        L, B, d, H, has_mlp, batch_first, xshape, has_in_b = ctx.dims
-        M = L * B
-        s = ctx.saved
-        x0, mean1, rstd1, a, qkv, o, lse, x1 = s[:8]
-        ln1_w, in_w, out_w = ctx.params[:3]
-        dx2 = _as_rows_f32(dy).view(M, d)
-        mlp_grads = ()
-        if has_mlp:
-            mean2, rstd2, b, u, g = s[8:]
-            ln2_w, _, fc_w, _, proj_w, _ = ctx.params[3:]
-            dv = ops.cast_bf16(dx2)
-            d_proj_w, d_proj_b = ops.gemm_wgrad(dv, g, want_bias=True)
-            du = ops.gemm_dgrad_dgelu(dv, bf16_of(proj_w), u)
-            d_fc_w, d_fc_b = ops.gemm_wgrad(du, b, want_bias=True)
-            db = ops.gemm_dgrad(du, bf16_of(fc_w))
-            dx1, dx1_16, d_ln2_w, d_ln2_b = ops.layernorm_bwd(db, x1, mean2, rstd2, gamma=_f32c(ln2_w), dres=dx2,
-                                                              want_bf16=True, affine_grads=True)
-            mlp_grads = (d_ln2_w, d_ln2_b, d_fc_w, d_fc_b, d_proj_w, d_proj_b)
+        B, L, d, H, has_mlp, batch_first, xshape = ctx.dims
+        dx = _as_rows_f32(dy).view(L * B, d)
+        twin = getattr(dy, "_b200_bf16_twin", None)
+        dx16 = None
+        if twin is not None and twin[1] == dy._version and dy.dtype == F32 and dy.is_contiguous() and twin[0].shape == dy.shape:
+            dx16 = twin[0].view(L * B, d)
+        grads = []
+        for i in range(len(ctx.layers) - 1, -1, -1):
+            need_dx = i > 0 or ctx.x_needs_grad
+            dx, dx16, g = rab_layer_backward(dx, dx16, ctx.saved_all[i], ctx.layers[i], B, L, H, not batch_first, has_mlp,
+                                             need_dx, ctx.sink)
+            ctx.saved_all[i] = None
+            grads.append(g)
+        flat = []
+        for g in reversed(grads):
+            flat.extend(g)
+        ctx.saved_all = None
+        return (dx.view(xshape) if dx is not None else None, None, None, None, *flat)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Token-sequence assembly + the LayerNorms around the stack of blocks.TiTokEncoder / TiTokDecoder (blocks.py:254-282, 337-361)
+# ------------------------------------------------------------------------------------------------------------
+class TokensAssembleFn(torch.autograd.Function):
+    """tokens[B, extra + P + tail, d] fp32 (batch-first) of the blocks.py encoder / decoder front ends in one GEMM + one pass:
+
+      encoder (blocks.py:257-267): src = image [B, C, H, W], patch > 0: rows [1, 1+P) = patch_embed(image) + positional_embedding[1:],
+               row 0 = class_embedding + positional_embedding[0], tail = latent_tokens + latent_token_positional_embedding
+      decoder (blocks.py:340-352): src = latents [B, P, K], patch == 0: rows [extra, extra+P) = decoder_embed(latents) +
+               latent_token_positional_embedding, head rows = [class_embedding; mask_token x grid^2] + positional_embedding
+
+    weight is the Conv2d [d, C, p, p] / Linear [d, K] weight.  Every broadcast row and positional table gets its gradient
+    from one batch reduction of the token gradient (tokens_assemble_bwd_reduce)."""
+
+    @staticmethod
+    def forward(ctx, src, weight, bias, pos, head0, head1, head_pos, tail_a, tail_b, patch):
+        d = weight.shape[0]
+        if patch > 0:
+            B, C, H, W = src.shape
+            cols = ops.im2col_bf16(_as_rows_f32(src), patch)
+            P = (H // patch) * (W // patch)
+            K = Kp = C * patch * patch
+            w16 = bf16_of(weight).view(d, K)
         else:
-            dx1, dx1_16 = dx2, ops.cast_bf16(dx2)
-        d_out_w, d_out_b = ops.gemm_wgrad(dx1_16, o.view(M, d), want_bias=True)
-        do = ops.gemm_dgrad(dx1_16, bf16_of(out_w))
-        dqkv = ops.flash_attn_bwd(qkv, o, do.view(xshape), lse, B, L, H, False, seq_first=not batch_first).view(M, -1)
-        d_in_w, d_in_b = ops.gemm_wgrad(dqkv, a, want_bias=True)
-        da = ops.gemm_dgrad(dqkv, bf16_of(in_w))
-        dx0, _, d_ln1_w, d_ln1_b = ops.layernorm_bwd(da, x0, mean1, rstd1, gamma=_f32c(ln1_w), dres=dx1,
-                                                     want_bf16=False, affine_grads=True)
+            B, P, K = src.shape
+            Kp = (K + 7) // 8 * 8
+            cols = _pad_cols(src.detach().reshape(B * P, K).to(BF16), Kp).contiguous()
+            w16 = _pad_cols(bf16_of(weight), Kp).contiguous()
+        extra = 0 if head_pos is None else head_pos.shape[0]
+        tail = 0 if tail_a is None else tail_a.shape[0]
+        tokens = ops.tokens_assemble_fwd(cols, w16, _f32c(bias), _f32c(pos), _f32c(head0), _f32c(head1), _f32c(head_pos),
+                                         _f32c(tail_a), _f32c(tail_b), B, P, extra, tail)
+        ctx.saved = (cols, w16)
+        ctx.dims = (tuple(src.shape), patch, P, K, Kp, d, extra, tail, tuple(weight.shape))
+        ctx.flags = (src.requires_grad, bias is not None, head1 is not None, tail_b is not None)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, dtokens):
+        cols, w16 = ctx.saved
+        sshape, patch, P, K, Kp, d, extra, tail, wshape = ctx.dims
+        src_grad, has_bias, has_head1, has_tail_b = ctx.flags
+        dsum, dpe = ops.tokens_assemble_bwd_reduce(_as_rows_f32(dtokens), extra, tail)
+        dW = ops.gemm_wgrad(dpe, cols)
+        dW = (dW[:, :K] if Kp != K else dW).reshape(wshape)
+        dpos = dsum[extra:extra + P]
+        db = ops.colsum_f32(dpos.contiguous()) if has_bias else None
+        d_head0 = dsum[0:1] if extra > 0 else None
+        d_head1 = ops.colsum_f32(dsum[1:extra].contiguous()).view(1, d) if (has_head1 and extra > 1) else None
+        d_head_pos = dsum[:extra] if extra > 0 else None
+        d_tail = dsum[extra + P:] if tail > 0 else None
+        dsrc = None
+        if src_grad:
+            dcols = ops.gemm_dgrad(dpe, w16)
+            if patch > 0:
+                B, C, H, W = sshape
+                dsrc = ops.col2im(dcols, B, C, H, W, patch)
+            else:
+                dsrc = dcols[:, :K].float().reshape(sshape)
         ctx.saved = None
-        return (dx0.view(xshape), None, None, None, d_ln1_w, d_ln1_b, d_in_w, (d_in_b if has_in_b else None), d_out_w, d_out_b,
-                *mlp_grads)
+        return dsrc, dW, db, dpos, d_head0, d_head1, d_head_pos, d_tail, (d_tail if has_tail_b else None), None
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm (affine) fp32 -> fp32 on a token range x[:, t0:t0+cnt] of x [B, N, d]: ln_pre over the whole sequence
+    (t0 = 0, cnt = N; blocks.py:269,353) and ln_post over the latent / patch tokens only (blocks.py:275-276, 358-359) -- the
+    range is gathered by the kernel's caller and its gradient scattered back with the bf16 twin the stack's backward wants."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, t0, cnt, eps):
+        B, N, d = x.shape
+        xf = _as_rows_f32(x)
+        rows = xf if (t0 == 0 and cnt == N) else ops.gather_tokens_f32(xf, t0, cnt)
+        _, y, mean, rstd, _ = ops.layernorm_fwd(rows.view(B * cnt, d), gamma=_f32c(weight), beta=_f32c(bias), out_bf16=False,
+                                                out_f32=True, eps=eps)
+        ctx.saved = (rows, mean, rstd, weight)
+        ctx.dims = (B, N, d, t0, cnt)
+        ctx.x_needs_grad = x.requires_grad
+        return y.view(B, cnt, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        rows, mean, rstd, weight = ctx.saved
+        B, N, d, t0, cnt = ctx.dims
+        drows, _, dg, db = ops.layernorm_bwd(_as_rows_f32(dy).view(B * cnt, d), rows.view(B * cnt, d), mean, rstd,
+                                             gamma=_f32c(weight), want_bf16=False, affine_grads=True)
+        dx = None
+        if ctx.x_needs_grad:
+            if t0 == 0 and cnt == N:
+                dx = drows.view(B, N, d)
+            else:
+                dx, dx16 = ops.scatter_tokens(drows, B, N, t0, cnt, want_bf16=True)
+                dx._b200_bf16_twin = (dx16, dx._version)
+        ctx.saved = None
+        return dx, dg, db, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -396,14 +396,16 @@ class ResidualAttentionBlock(nn.Module):
                 ("c_proj", nn.Linear(mlp_width, d_model)),
             ]))
 
-    def forward(self, x):
-        mlp = ()
+    def _params(self):
+        p = (self.ln_1.weight, self.ln_1.bias, self.attn.in_proj_weight, self.attn.in_proj_bias,
+             self.attn.out_proj.weight, self.attn.out_proj.bias)
         if self.mlp_ratio > 0:
-            mlp = (self.ln_2.weight, self.ln_2.bias, self.mlp.c_fc.weight, self.mlp.c_fc.bias,
-                   self.mlp.c_proj.weight, self.mlp.c_proj.bias)
-        return Fn.ResidualAttentionBlockFn.apply(x, self.n_head, self.mlp_ratio > 0, False, self.ln_1.weight, self.ln_1.bias,
-                                                 self.attn.in_proj_weight, self.attn.in_proj_bias,
-                                                 self.attn.out_proj.weight, self.attn.out_proj.bias, *mlp)
+            p += (self.ln_2.weight, self.ln_2.bias, self.mlp.c_fc.weight, self.mlp.c_fc.bias,
+                  self.mlp.c_proj.weight, self.mlp.c_proj.bias)
+        return p
+
+    def forward(self, x):
+        return Fn.ResidualAttentionStackFn.apply(x, self.n_head, self.mlp_ratio > 0, False, *self._params())
 
 
 class _UViTAttention(nn.Module):
@@ -459,10 +461,113 @@ class UViTBlock(nn.Module):
     def forward(self, x, skip=None):
         if self.skip_linear is not None:
             x = Fn.LinearFn.apply(torch.cat([x, skip], dim=-1), self.skip_linear.weight, self.skip_linear.bias, False)
-        return Fn.ResidualAttentionBlockFn.apply(x, self.attn.num_heads, True, True, self.norm1.weight, self.norm1.bias,
+        return Fn.ResidualAttentionStackFn.apply(x, self.attn.num_heads, True, True, self.norm1.weight, self.norm1.bias,
                                                  self.attn.qkv.weight, self.attn.qkv.bias, self.attn.proj.weight,
                                                  self.attn.proj.bias, self.norm2.weight, self.norm2.bias,
                                                  self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias)
+
+
+_BLOCKS_SIZES = {"small": (512, 8, 8), "base": (768, 12, 12), "large": (1024, 24, 16)}   # width, layers, heads (blocks.py:219-233)
+
+
+def _run_rab_stack(blocks, x, n_heads):
+    """x [B, N, d] fp32 (batch-first: the drop-ins never materialise the reference's NLD -> LND permute, blocks.py:270,273)."""
+    params = []
+    for blk in blocks:
+        params.extend(blk._params())
+    return Fn.ResidualAttentionStackFn.apply(x, n_heads, True, True, *params)
+
+
+class BlocksTiTokEncoder(nn.Module):
+    """blocks.TiTokEncoder (blocks.py:208-282) -- exported as `blocks.TiTokEncoder` by shim/blocks.py.  Same constructor
+    (`config` with image_size, patch_size, transformer in {small, base, large}, latent_tokens, latent_dim), same parameters
+    and state_dict keys, same forward(pixel_values, latent_tokens) -> [B, latent_dim, 1, latent_tokens].
+
+    The whole front end of blocks.py:257-270 -- patch_embed conv, reshape / permute, class-token cat, positional add,
+    latent tokens + their positions, cat -- is one im2col + one tcgen05 GEMM whose epilogue writes the patch rows of the
+    [B, 1 + grid^2 + latent, d] sequence and one pass for the broadcast rows (TokensAssembleFn); ln_pre, the block stack (one
+    autograd node, batch-first) and ln_post on the latent tokens only follow; conv_out (1x1) is a skinny GEMM."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.image_size = config.image_size
+        self.patch_size = config.patch_size
+        self.grid_size = self.image_size // self.patch_size
+        self.model_size = config.transformer
+        self.num_latent_tokens = config.latent_tokens
+        self.token_size = config.latent_dim
+        self.width, self.num_layers, self.num_heads = _BLOCKS_SIZES[self.model_size]
+        self.patch_embed = nn.Conv2d(in_channels=3, out_channels=self.width, kernel_size=self.patch_size,
+                                     stride=self.patch_size, bias=True)
+        scale = self.width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(1, self.width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(self.grid_size ** 2 + 1, self.width))
+        self.latent_token_positional_embedding = nn.Parameter(scale * torch.randn(self.num_latent_tokens, self.width))
+        self.ln_pre = nn.LayerNorm(self.width)
+        self.transformer = nn.ModuleList([ResidualAttentionBlock(self.width, self.num_heads, mlp_ratio=4.0)
+                                          for _ in range(self.num_layers)])
+        self.ln_post = nn.LayerNorm(self.width)
+        self.conv_out = nn.Conv2d(self.width, self.token_size, kernel_size=1, bias=True)
+
+    def forward(self, pixel_values, latent_tokens):
+        B, P, L = pixel_values.shape[0], self.grid_size ** 2, self.num_latent_tokens
+        pos = self.positional_embedding
+        tokens = Fn.TokensAssembleFn.apply(pixel_values, self.patch_embed.weight, self.patch_embed.bias, pos[1:], self.class_embedding,
+                                           None, pos[:1], latent_tokens, self.latent_token_positional_embedding, self.patch_size)
+        x = Fn.LayerNormFn.apply(tokens, self.ln_pre.weight, self.ln_pre.bias, 0, 1 + P + L, self.ln_pre.eps)
+        x = _run_rab_stack(self.transformer, x, self.num_heads)
+        lat = Fn.LayerNormFn.apply(x, self.ln_post.weight, self.ln_post.bias, 1 + P, L, self.ln_post.eps)     # [B, L, d]
+        y = Fn.LinearFn.apply(lat, self.conv_out.weight.view(self.token_size, self.width), self.conv_out.bias, False)
+        return y.permute(0, 2, 1).unsqueeze(2)                                    # [B, token_size, 1, L] (blocks.py:281)
+
+
+class BlocksTiTokDecoder(nn.Module):
+    """blocks.TiTokDecoder (blocks.py:285-361) -- exported as `blocks.TiTokDecoder` by shim/blocks.py.  decoder_embed + the
+    mask-token / class-token / positional assembly of blocks.py:341-352 is one GEMM + one pass (TokensAssembleFn), ln_pre, the
+    block stack, ln_post on the grid tokens, and `ffn` (1x1 conv + pixel-shuffle Rearrange) as the de-patchify GEMM whose
+    epilogue stores the NCHW image.  The final 3x3 `conv_out` (blocks.py:334,361) is an ordinary padded convolution outside
+    the §8 path and stays nn.Conv2d."""
+
+    def __init__(self, config):
+        super().__init__()
+        from einops.layers.torch import Rearrange
+        self.config = config
+        self.image_size = config.image_size
+        self.patch_size = config.patch_size
+        self.grid_size = self.image_size // self.patch_size
+        self.model_size = config.transformer
+        self.num_latent_tokens = config.latent_tokens
+        self.token_size = config.latent_dim
+        self.width, self.num_layers, self.num_heads = _BLOCKS_SIZES[self.model_size]
+        self.decoder_embed = nn.Linear(self.token_size, self.width, bias=True)
+        scale = self.width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(1, self.width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn(self.grid_size ** 2 + 1, self.width))
+        self.mask_token = nn.Parameter(scale * torch.randn(1, 1, self.width))
+        self.latent_token_positional_embedding = nn.Parameter(scale * torch.randn(self.num_latent_tokens, self.width))
+        self.ln_pre = nn.LayerNorm(self.width)
+        self.transformer = nn.ModuleList([ResidualAttentionBlock(self.width, self.num_heads, mlp_ratio=4.0)
+                                          for _ in range(self.num_layers)])
+        self.ln_post = nn.LayerNorm(self.width)
+        self.ffn = nn.Sequential(                                            # parameter container: ffn.0.{weight,bias}
+            nn.Conv2d(self.width, self.patch_size * self.patch_size * 3, 1, padding=0, bias=True),
+            Rearrange("b (p1 p2 c) h w -> b c (h p1) (w p2)", p1=self.patch_size, p2=self.patch_size))
+        self.conv_out = nn.Conv2d(3, 3, 3, padding=1, bias=True)
+
+    def forward(self, z_quantized):
+        N, C, H, W = z_quantized.shape
+        assert H == 1 and W == self.num_latent_tokens, f"{H}, {W}, {self.num_latent_tokens}"
+        P = self.grid_size ** 2
+        lat = z_quantized.reshape(N, C * H, W).permute(0, 2, 1)                    # [B, L, token_size]
+        tokens = Fn.TokensAssembleFn.apply(lat, self.decoder_embed.weight, self.decoder_embed.bias,
+                                           self.latent_token_positional_embedding[:W], self.class_embedding,
+                                           self.mask_token.view(1, self.width), self.positional_embedding, None, None, 0)
+        x = Fn.LayerNormFn.apply(tokens, self.ln_pre.weight, self.ln_pre.bias, 0, 1 + P + W, self.ln_pre.eps)
+        x = _run_rab_stack(self.transformer, x, self.num_heads)
+        x = Fn.LayerNormFn.apply(x, self.ln_post.weight, self.ln_post.bias, 1, P, self.ln_post.eps)            # [B, P, d]
+        img = Fn.DepatchifyFn.apply(x, self.ffn[0].weight, self.ffn[0].bias, self.grid_size, self.grid_size, self.patch_size)
+        return self.conv_out(img)
 
 
 class VectorQuantizer(nn.Module):

@@ -19,7 +19,8 @@ launch_count = 0  # number of C-ABI compute calls issued (bench.py reports it as
 
 
 # kernels launched per C-ABI call (memsets not counted); everything else launches exactly one kernel
-_KERNELS_PER_CALL = {"b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3, "b200vit_cross_entropy_fwd": 2, "b200vit_embed_bwd": 2}
+_KERNELS_PER_CALL = {"b200vit_vq_fwd": 3, "b200vit_patch_embed_fwd": 3, "b200vit_cross_entropy_fwd": 2, "b200vit_embed_bwd": 2,
+                     "b200vit_tokens_assemble_fwd": 2, "b200vit_affine_unfold_grads": 2}
 
 _prof = None  # list of (start_event, end_event, flops) while profile_gemms() is active
 
@@ -405,6 +406,61 @@ def patch_embed_bwd_reduce(dtokens, extra):
     dpe = torch.empty(B * (T - extra), d, device=dtokens.device, dtype=BF16)
     _call("b200vit_patch_embed_bwd_reduce", dtokens, ptr(_chk(dtokens, F32, "dtokens")), ptr(dsum), ptr(dpe), B, T, extra, d, stream_ptr())
     return dsum, dpe
+
+
+def tokens_assemble_fwd(cols, w_bf16, bias, pos, head0, head1, head_pos, tail_a, tail_b, B, P, extra, tail):
+    """tokens[B, extra + P + tail, d] fp32 of blocks.TiTokEncoder / TiTokDecoder (blocks.py:254-268, 337-352): GEMM rows
+    cols[B*P, K] x w[d, K]^T + bias + pos[P, d] at rows [extra, extra+P), broadcast head / tail rows around them."""
+    K = cols.shape[1]
+    d = w_bf16.shape[0]
+    tokens = torch.empty(B, extra + P + tail, d, device=cols.device, dtype=F32)
+    _call("b200vit_tokens_assemble_fwd", cols, ptr(_chk(cols, BF16, "cols")), ptr(_chk(w_bf16, BF16, "w")), ptr(bias), ptr(_chk(pos, F32, "pos")),
+          ptr(head0), ptr(head1), ptr(head_pos), ptr(tail_a), ptr(tail_b), ptr(tokens), B, P, K, d, extra, tail, stream_ptr(),
+          flops=2.0 * B * P * K * d)
+    return tokens
+
+
+def tokens_assemble_bwd_reduce(dtokens, extra, tail):
+    B, T, d = dtokens.shape
+    P = T - extra - tail
+    dsum = torch.empty(T, d, device=dtokens.device, dtype=F32)
+    dpe = torch.empty(B * P, d, device=dtokens.device, dtype=BF16)
+    _call("b200vit_tokens_assemble_bwd_reduce", dtokens, ptr(_chk(dtokens, F32, "dtokens")), ptr(dsum), ptr(dpe), B, T, extra, tail, d,
+          stream_ptr())
+    return dsum, dpe
+
+
+def gather_tokens_f32(x, t0=0, cnt=1):
+    """x [B, N, d] fp32 -> fp32 [B, cnt, d] copy of tokens t0 .. t0+cnt-1."""
+    B, N, d = x.shape
+    out = torch.empty(B, cnt, d, device=x.device, dtype=F32)
+    _call("b200vit_gather_tokens_f32", x, ptr(_chk(x, F32, "x")), ptr(out), B, N, d, t0, cnt, stream_ptr())
+    return out
+
+
+def affine_fold(W, bias, gamma, beta, out=None):
+    """(bf16(W * gamma) [N, K], bias + W beta [N]): the affine LayerNorm in front of a Linear folded into its weights."""
+    N, K = W.shape
+    if out is None:
+        out = (torch.empty(N, K, device=W.device, dtype=BF16), torch.empty(N, device=W.device, dtype=F32))
+    _call("b200vit_affine_fold", W, ptr(_chk(W, F32, "W")), ptr(bias), ptr(_chk(gamma, F32, "gamma")), ptr(_chk(beta, F32, "beta")),
+          ptr(out[0]), ptr(out[1]), N, K, stream_ptr())
+    return out
+
+
+def affine_unfold_grads(dW, W, gamma, beta, dbias, dgamma=None, dbeta=None, accumulate=False):
+    """In place dW <- dW * gamma + dbias (x) beta (dW, dbias = wgrad / bias gradient on xhat); returns (dgamma, dbeta)."""
+    N, K = W.shape
+    if dgamma is None:
+        dgamma = torch.empty(K, device=W.device, dtype=F32)
+        dbeta = torch.empty(K, device=W.device, dtype=F32)
+        accumulate = False
+    lib = _cabi.lib_for(W)
+    ws_bytes = lib.b200vit_affine_unfold_workspace_size(K)
+    ws = torch.empty(ws_bytes // 4, device=W.device, dtype=F32)
+    _call("b200vit_affine_unfold_grads", W, ptr(_chk(dW.view(N, K), F32, "dW")), ptr(_chk(W, F32, "W")), ptr(_chk(gamma, F32, "gamma")),
+          ptr(_chk(beta, F32, "beta")), ptr(_chk(dbias, F32, "dbias")), ptr(dgamma), ptr(dbeta), N, K, 1 if accumulate else 0, ptr(ws), ws_bytes, stream_ptr())
+    return dgamma, dbeta
 
 
 def im2col_bf16(x, p):

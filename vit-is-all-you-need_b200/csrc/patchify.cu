@@ -75,14 +75,57 @@ __global__ void broadcast_extra_kernel(const float* __restrict__ extra_emb, floa
   }
 }
 
+// Rows of the [B, T, d] token buffer that do not come out of the GEMM (blocks.py:261-267, 346-352):
+//   head rows e in [0, extra):      out[b, e]             = (e == 0 ? head0 : head1)[0, :] + head_pos[e, :]
+//                                   (class_embedding / mask_token + positional_embedding rows)
+//   tail rows l in [0, tail):       out[b, extra + P + l] = tail_a[l, :] + tail_b[l, :]   (latent_tokens + their positions)
+// head_pos / tail_b may be null.  (train_vit.ViT's extra_emb rows keep broadcast_extra_kernel above.)
+__global__ void assemble_rows_kernel(const float* __restrict__ head0, const float* __restrict__ head1,
+                                     const float* __restrict__ head_pos, const float* __restrict__ tail_a,
+                                     const float* __restrict__ tail_b, float* __restrict__ out, int B, int T, int extra,
+                                     int P, int tail, int d) {
+  const int nvec = d / 4, per = extra + tail;
+  const long long total = (long long)B * per * nvec;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % nvec);
+    const int e = (int)((t / nvec) % per);
+    const long long b = t / ((long long)nvec * per);
+    float4 v, w = make_float4(0.f, 0.f, 0.f, 0.f);
+    int row;
+    if (e < extra) {
+      v = __ldg(reinterpret_cast<const float4*>(e == 0 ? head0 : head1) + c4);
+      if (head_pos != nullptr) w = __ldg(reinterpret_cast<const float4*>(head_pos + (long long)e * d) + c4);
+      row = e;
+    } else {
+      const int l = e - extra;
+      v = __ldg(reinterpret_cast<const float4*>(tail_a + (long long)l * d) + c4);
+      if (tail_b != nullptr) w = __ldg(reinterpret_cast<const float4*>(tail_b + (long long)l * d) + c4);
+      row = extra + P + l;
+    }
+    reinterpret_cast<float4*>(out + (b * T + row) * d)[c4] = make_float4(v.x + w.x, v.y + w.y, v.z + w.z, v.w + w.w);
+  }
+}
+
+// out[b, j, :] = x[b, t0 + j, :] (fp32 copy of a token range: the ln_post input of the blocks.py encoder / decoder)
+__global__ void gather_rows_f32_kernel(const float* __restrict__ x, float* __restrict__ out, int B, long long in_stride,
+                                       long long out_stride, long long in_off) {
+  const long long per = out_stride / 4;
+  const long long total = (long long)B * per;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long b = t / per, c = t - b * per;
+    reinterpret_cast<float4*>(out + b * out_stride)[c] = __ldg(reinterpret_cast<const float4*>(x + b * in_stride + in_off) + c);
+  }
+}
+
 // Backward helpers on the fp32 token gradient dtok[B, T, d]:
 //   dsum[t, :]  = sum_b dtok[b, t, :]          (-> extra_emb.grad rows [0,extra), pos_emb.grad rows [extra,T))
 //   dpe[(b,p),:] = bf16(dtok[b, extra + p, :]) (compact operand of the conv wgrad GEMM)
+// (P = rows of each image that came out of the GEMM: T - extra for train_vit.ViT, T - extra - tail for the blocks.py
+// encoder / decoder whose latent tokens follow the patches)
 __global__ void patch_bwd_reduce_kernel(const float* __restrict__ dtok, float* __restrict__ dsum,
-                                        __nv_bfloat16* __restrict__ dpe, int B, int T, int extra, int d) {
+                                        __nv_bfloat16* __restrict__ dpe, int B, int T, int extra, int P, int d) {
   const int nvec = d / 4;
   const long long total = (long long)T * nvec;
-  const int P = T - extra;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(t % nvec);
     const int tok = (int)(t / nvec);
@@ -90,7 +133,7 @@ __global__ void patch_bwd_reduce_kernel(const float* __restrict__ dtok, float* _
     for (int b = 0; b < B; ++b) {
       const float4 v = reinterpret_cast<const float4*>(dtok + ((long long)b * T + tok) * d)[c4];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      if (dpe != nullptr && tok >= extra) {
+      if (dpe != nullptr && tok >= extra && tok < extra + P) {
         uint2 w;
         w.x = pack_bf16(v.x, v.y); w.y = pack_bf16(v.z, v.w);
         *reinterpret_cast<uint2*>(dpe + ((long long)b * P + (tok - extra)) * d + c4 * 4) = w;
@@ -188,7 +231,44 @@ int b200vit_patch_embed_bwd_reduce(const float* dtokens, float* dsum, void* dpe_
                                    void* stream) {
   B200_REQUIRE(dtokens && dsum && d % 4 == 0 && T > extra, "patch_embed_bwd_reduce: bad arguments");
   patch_bwd_reduce_kernel<<<grid_for((long long)T * (d / 4), 128), 128, 0, (cudaStream_t)stream>>>(
-      dtokens, dsum, (__nv_bfloat16*)dpe_bf16, B, T, extra, d);
+      dtokens, dsum, (__nv_bfloat16*)dpe_bf16, B, T, extra, T - extra, d);
+  B200_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int b200vit_tokens_assemble_fwd(const void* cols_bf16, const void* w_bf16, const float* bias, const float* pos,
+                                const float* head0, const float* head1, const float* head_pos, const float* tail_a,
+                                const float* tail_b, float* tokens, int B, int P, int K, int d, int extra, int tail,
+                                void* stream) {
+  B200_REQUIRE(cols_bf16 && w_bf16 && pos && tokens && B > 0 && P > 0, "tokens_assemble_fwd: bad arguments");
+  B200_REQUIRE(d % 8 == 0 && K % 8 == 0, "tokens_assemble_fwd: d=%d and K=%d must be multiples of 8", d, K);
+  B200_REQUIRE(extra >= 0 && tail >= 0 && (extra == 0 || head0) && (extra <= 1 || head1) && (tail == 0 || tail_a),
+               "tokens_assemble_fwd: head / tail rows requested without their sources");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int T = extra + P + tail;
+  if (extra + tail > 0) {
+    assemble_rows_kernel<<<grid_for((long long)B * (extra + tail) * (d / 4), 256), 256, 0, st>>>(
+        head0, head1, head_pos, tail_a, tail_b, tokens, B, T, extra, P, tail, d);
+    B200_CUDA(cudaGetLastError());
+  }
+  return gemm_patch_epilogue(cols_bf16, w_bf16, bias, pos, tokens, B * P, d, K, P, T, extra, st);
+}
+
+int b200vit_tokens_assemble_bwd_reduce(const float* dtokens, float* dsum, void* dpe_bf16, int B, int T, int extra, int tail,
+                                       int d, void* stream) {
+  B200_REQUIRE(dtokens && dsum && d % 4 == 0 && extra >= 0 && tail >= 0 && T > extra + tail,
+               "tokens_assemble_bwd_reduce: bad arguments");
+  patch_bwd_reduce_kernel<<<grid_for((long long)T * (d / 4), 128), 128, 0, (cudaStream_t)stream>>>(
+      dtokens, dsum, (__nv_bfloat16*)dpe_bf16, B, T, extra, T - extra - tail, d);
+  B200_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int b200vit_gather_tokens_f32(const float* x, float* out, int B, int N, int d, int t0, int cnt, void* stream) {
+  B200_REQUIRE(x && out && B > 0 && N > 0 && d > 0 && d % 4 == 0 && t0 >= 0 && cnt > 0 && t0 + cnt <= N,
+               "gather_tokens_f32: bad arguments (d must be a multiple of 4, 0 <= t0, t0 + cnt <= N)");
+  gather_rows_f32_kernel<<<grid_for((long long)B * cnt * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      x, out, B, (long long)N * d, (long long)cnt * d, (long long)t0 * d);
   B200_CUDA(cudaGetLastError());
   return OK;
 }

@@ -1,14 +1,15 @@
 """Drop-in for the reference's top-level module `blocks`.
 
-The hot-path classes (ResidualAttentionBlock blocks.py:32-70, UViTBlock blocks.py:174-201, VectorQuantizer blocks.py:405-505) come from
-b200vit.modules; everything else the reference's blocks.py defines (TiTokEncoder / TiTokDecoder blocks.py:208-361,
-...) is taken from the reference's own file, executed in this module's namespace, so that
-`from blocks import TiTokEncoder, TiTokDecoder, VectorQuantizer` (train_tatitok.py:13) keeps working and the encoder /
-decoder assemble themselves out of the sm_100a-backed blocks (they look `ResidualAttentionBlock` up by its module-global
-name when they are constructed)."""
+The hot-path classes (ResidualAttentionBlock blocks.py:32-70, UViTBlock blocks.py:174-201, TiTokEncoder / TiTokDecoder
+blocks.py:208-361 with the fused token-sequence assembly, VectorQuantizer blocks.py:405-505) come from b200vit.modules;
+everything else the reference's blocks.py defines (TATiTokDecoder, the dead UViT helpers ...) is taken from the reference's own
+file, executed in this module's namespace, so that `from blocks import TiTokEncoder, TiTokDecoder, VectorQuantizer`
+(train_tatitok.py:13) keeps working."""
 import os
 import sys
 
+from b200vit.modules import BlocksTiTokDecoder as _DEC
+from b200vit.modules import BlocksTiTokEncoder as _ENC
 from b200vit.modules import ResidualAttentionBlock as _RAB
 from b200vit.modules import UViTBlock as _UVB
 from b200vit.modules import VectorQuantizer as _VQ
@@ -22,5 +23,7 @@ for _p in sys.path:
         break
 
 ResidualAttentionBlock = _RAB
+TiTokEncoder = _ENC
+TiTokDecoder = _DEC
 VectorQuantizer = _VQ
 UViTBlock = _UVB
