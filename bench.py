@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """ViT-B/16 224px bf16 training throughput on 1..8 B200s (BASELINE.json configs[1]) through the drop-in modules.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]        # our arm
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B]        # our arm (the headline: --workload vit_b)
+    python bench.py --workload {vit_l,vit_ti,titok_s,tatitok_s,videogpt_b,vq} ...   # the other configs (bench_workloads.py)
     python bench.py --impl reference ...      # the reference's own CPU path (unmodified modules from baseline/_ref)
 
 One "step" = forward + cross-entropy + backward + AdamW on a per-GPU batch of synthetic images (weak scaling).
@@ -473,7 +474,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (weak scaling); default: the workload's (256 for vit_b)")
+    ap.add_argument("--workload", type=str, default="vit_b", choices=["vit_b", "vit_l", "vit_ti", "titok_s", "tatitok_s", "videogpt_b", "vq"],
+                    help="vit_b (default) = BASELINE.json configs[1], the headline; the others are the remaining configs through the "
+                         "same JSON contract (bench_workloads.py)")
     ap.add_argument("--bucket-mb", type=float, default=32.0)
     ap.add_argument("--impl", type=str, default="b200vit", choices=["b200vit", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU-baseline sample (a few seconds per step)")
@@ -485,8 +489,14 @@ def main():
     ap.add_argument("--optimizer", type=str, default="b200vit", choices=["b200vit", "torch-fused"],
                     help="AdamW implementation inside the step (default: the fused kernel of this library)")
     args = ap.parse_args()
+    args.batch_given = args.batch is not None
+    if args.batch is None:
+        args.batch = 256
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload != "vit_b":
+        import bench_workloads
+        return bench_workloads.run(args)
     return run_gpu_arm(args)
 
 
