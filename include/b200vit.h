@@ -55,6 +55,16 @@ int b200vit_gemm_dgrad(const void* dy, const void* w, void* dx, int M, int N, in
  * gprime = GELU'(u) as written by b200vit_gemm_bias_gelu */
 int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* gprime, void* dx, int M, int N,
                              int K, void* stream);
+/* The two GELU GEMMs above with GELU'(u) carried as an 8-bit fixed-point code instead of bf16:
+ *   code = round((GELU'(u) - lo) / step), step = 1.27 / 255, lo = -27 step (GELU' lies in [-0.129, 1.129] for every u), decoded
+ *   as lo + step * code: absolute error <= step / 2 = 0.0025.  Both kernels are bounded by the HBM bytes of this very tensor;
+ *   the code halves them (fc1 forward writes [M, 4d] bytes less, its backward twin reads them less).  gprime_q8: uint8 [M, N]. */
+int b200vit_gemm_bias_gelu_q8(const void* x, const void* w, const float* bias, void* g, void* gprime_q8, int M, int N, int K,
+                              void* stream);
+int b200vit_gemm_dgrad_dgelu_q8(const void* dy, const void* w, const void* gprime_q8, void* dx, int M, int N, int K,
+                                void* stream);
+float b200vit_gelu_grad_code_lo(void);
+float b200vit_gelu_grad_code_step(void);
 /* dw[N,K](f32) (+)= dy[M,N]^T x[M,K]                   autograd of nn.Linear wrt weight              */
 int b200vit_gemm_wgrad(const void* dy, const void* x, float* dw, int M, int N, int K, int accumulate,
                        void* stream);
@@ -103,6 +113,8 @@ int b200vit_layernorm_bwd_xhat(const void* dy_bf16, const void* xhat_bf16, const
 int b200vit_colsum_bf16(const void* a, float* out, int M, int N, int accumulate, void* stream);
 int b200vit_colsum_f32(const float* a, float* out, int rows, int n, void* stream);
 int b200vit_cast_f32_bf16(const float* in, void* out, long long n, void* stream);
+/* out(f32)[n] = scale * in(bf16)[n]: gradients coming back from a bf16-compressed all-reduce (b200vit/ddp.py)            */
+int b200vit_cast_bf16_f32(const void* in, float* out, long long n, float scale, void* stream);
 /* out(bf16) = x(f32) * keep / (1 - p): backward of nn.Dropout (transformer.py:40) fused with the cast that feeds the
  * fc2 dgrad / wgrad GEMMs; same mask function as b200vit_gemm_bias_dropout_residual                          */
 int b200vit_dropout_cast_bf16(const float* x, void* out_bf16, long long M, int d, float p, unsigned int seed,

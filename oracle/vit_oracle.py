@@ -86,6 +86,22 @@ def gelu_bwd(dg, u):
     return (dg * (cdf + u * pdf)).astype(u.dtype)
 
 
+# The CUDA path keeps GELU'(u) for backward as an 8-bit fixed-point code (csrc/gemm_tcgen05.cuh GP_LO / GP_STEP): the
+# derivative of nn.GELU() (transformer.py:38) lies in [-0.129, 1.129] for every u.  Restated here so that tests can check the
+# kernel's codes and bound the error the code adds (<= GELU_GRAD_STEP / 2 absolute).
+GELU_GRAD_STEP = 1.27 / 255.0
+GELU_GRAD_LO = -27.0 * GELU_GRAD_STEP
+
+
+def gelu_grad_code(u):
+    gp = gelu_bwd(np.ones_like(u), u)
+    return np.clip(np.rint((gp - GELU_GRAD_LO) / GELU_GRAD_STEP), 0, 255).astype(np.uint8)
+
+
+def gelu_grad_decode(code):
+    return GELU_GRAD_LO + GELU_GRAD_STEP * code.astype(np.float64)
+
+
 # ------------------------------------------------------------------------------------------------
 # F.scaled_dot_product_attention(q,k,v, attn_mask=-inf upper triangle or None) (transformer.py:22-28)
 # q,k,v: [B,h,N,hd]; scale 1/sqrt(hd); dropout_p = 0 (parity is only defined at p = 0)

@@ -99,6 +99,66 @@ check("TiTok (enc + VQ + dec)", lambda: M.TiTok(_TiTokCfg(32, 4, 8, 64, 12, "XS2
 check("VideoGPT", lambda: M.VideoGPT(_GPTCfg()),
       lambda: torch.randint(0, 64, (2 * world, 4, 16), generator=gg).to(dev),
       lambda m, xb: m(xb)[1])
+
+
+# ---- blocks.py flavour: the ResidualAttentionBlock stack delivers its (LayerNorm-folded) gradients through the bucket sink ----
+class _BlocksCfg:
+    image_size, patch_size, transformer, latent_tokens, latent_dim = 64, 16, "small", 8, 12
+
+
+class _TA(torch.nn.Module):     # encoder -> VectorQuantizer -> decoder as train_tatitok.TiTok wires them (train_tatitok.py:36-41)
+    def __init__(self):
+        super().__init__()
+        M._BLOCKS_SIZES["small"] = (128, 2, 2)     # a miniature "small" for this check only
+        self.encoder, self.decoder = M.BlocksTiTokEncoder(_BlocksCfg()), M.BlocksTiTokDecoder(_BlocksCfg())
+        self.latent_tokens = torch.nn.Parameter(128 ** -0.5 * torch.randn(8, 128))
+        self.quantize = M.VectorQuantizer(64, 12, 0.25, use_l2_norm=True)
+
+    def forward(self, x):
+        zq, info = self.quantize(self.encoder(x, self.latent_tokens))
+        return self.decoder(zq), info["quantizer_loss"]
+
+
+_small = M._BLOCKS_SIZES["small"]
+check("blocks.py TiTokEncoder + VectorQuantizer + TiTokDecoder", _TA,
+      lambda: torch.rand(4 * world, 3, 64, 64, generator=gg).to(dev),
+      lambda m, xb: (lambda out: torch.nn.functional.mse_loss(out[0], xb) + out[1])(m(xb)))
+M._BLOCKS_SIZES["small"] = _small
+
+# ---- gradient accumulation: a no_sync() micro-step followed by a synchronised one reduces the sum of both ----
+torch.manual_seed(0)
+ref = M.ViTClassifier(cfg, num_classes=10).to(dev)
+par = M.ViTClassifier(cfg, num_classes=10).to(dev)
+par.load_state_dict(ref.state_dict())
+wrapped = ddp.DataParallel(par, bucket_mb=4.0)
+x2 = torch.randn(B, 3, 64, 64, generator=g).to(dev)
+y2 = torch.randint(0, 10, (B,), generator=g).to(dev)
+with torch.autocast("cuda", dtype=torch.bfloat16):
+    (loss_fn(ref(x).float(), y) + loss_fn(ref(x2).float(), y2)).backward()
+    sl = slice(rank * 8, rank * 8 + 8)
+    with wrapped.no_sync():
+        loss_fn(wrapped(x[sl]).float(), y[sl]).backward()
+    loss_fn(wrapped(x2[sl]).float(), y2[sl]).backward()
+torch.cuda.synchronize()
+worst = max(((a.grad - b.grad).norm() / (a.grad.norm() + 1e-12)).item() for a, b in zip(ref.parameters(), par.parameters()))
+if rank == 0:
+    print(f"gradient accumulation (no_sync micro-step + synchronised step): max rel-L2 difference = {worst:.3e}")
+assert worst < 2e-2, worst
+
+# ---- bf16-compressed buckets: same check, tolerance = the bf16 rounding of the averaged gradient (2^-9 relative per element) ----
+torch.manual_seed(0)
+par = M.ViTClassifier(cfg, num_classes=10).to(dev)
+par.load_state_dict(ref.state_dict())
+wrapped = ddp.DataParallel(par, bucket_mb=4.0, compress_bf16=True)
+ref.zero_grad(set_to_none=True)
+with torch.autocast("cuda", dtype=torch.bfloat16):
+    loss_fn(ref(x).float(), y).backward()
+    loss_fn(wrapped(x[sl]).float(), y[sl]).backward()
+torch.cuda.synchronize()
+worst = max(((a.grad - b.grad).norm() / (a.grad.norm() + 1e-12)).item() for a, b in zip(ref.parameters(), par.parameters()))
+if rank == 0:
+    print(f"bf16-compressed all-reduce: max rel-L2 gradient difference = {worst:.3e}")
+assert worst < 2.5e-2, worst
 dist.destroy_process_group()
 if rank == 0:
     print("DDP gradient check OK")

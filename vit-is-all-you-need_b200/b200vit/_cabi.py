@@ -43,6 +43,10 @@ _SIGNATURES = {
     "b200vit_debug_max_clusters": (_I, []),
     "b200vit_gemm_bias": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "b200vit_gemm_bias_gelu": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200vit_gemm_bias_gelu_q8": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200vit_gemm_dgrad_dgelu_q8": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200vit_gelu_grad_code_lo": (_F, []),
+    "b200vit_gelu_grad_code_step": (_F, []),
     "b200vit_gemm_bias_residual": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "b200vit_gemm_bias_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "b200vit_gemm_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _P]),
@@ -64,6 +68,7 @@ _SIGNATURES = {
     "b200vit_colsum_bf16": (_I, [_P, _P, _I, _I, _I, _P]),
     "b200vit_colsum_f32": (_I, [_P, _P, _I, _I, _P]),
     "b200vit_cast_f32_bf16": (_I, [_P, _P, _L, _P]),
+    "b200vit_cast_bf16_f32": (_I, [_P, _P, _L, _F, _P]),
     "b200vit_patch_embed_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200vit_patch_embed_bwd_reduce": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "b200vit_tokens_assemble_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -31,6 +31,8 @@ from . import functional as Fn
 class _Bucket:
     def __init__(self, numel, device, dtype):
         self.flat = torch.zeros(numel, device=device, dtype=dtype)
+        self.flat16 = None     # bf16 staging of the compressed all-reduce (allocated on first use)
+        self.done = None       # event on the communication stream after the cast back (compressed path)
         self.params = []
         self.pending = 0
         self.work = None
@@ -38,8 +40,13 @@ class _Bucket:
 
 
 class DataParallel(torch.nn.Module):
-    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None):
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None, compress_bf16=None):
+        """compress_bf16 (default: environment B200VIT_DDP_BF16=1): each bucket crosses NVLink as bf16 -- cast on the
+        communication stream, all-reduced (average), cast back into the fp32 bucket -- i.e. half the bytes for the
+        collective, like torch's bf16_compress_hook; the optimizer still sees fp32 gradients."""
         super().__init__()
+        import os
+        self.compress_bf16 = (os.environ.get("B200VIT_DDP_BF16", "0") == "1") if compress_bf16 is None else bool(compress_bf16)
         self.module = module
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -177,7 +184,17 @@ class DataParallel(torch.nn.Module):
             ev.record(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ev)
-                b.work = self._all_reduce(b.flat)
+                if self.compress_bf16 and self.backend == "nccl":
+                    from . import ops
+                    if b.flat16 is None:
+                        b.flat16 = torch.empty(b.flat.numel(), device=b.flat.device, dtype=torch.bfloat16)
+                    ops.cast_bf16(b.flat, out=b.flat16)
+                    dist.all_reduce(b.flat16, op=dist.ReduceOp.AVG, group=self.pg, async_op=True).wait()   # comm stream waits
+                    ops.cast_f32_from_bf16(b.flat16, b.flat)
+                    b.done = torch.cuda.Event()
+                    b.done.record(self.comm_stream)
+                else:
+                    b.work = self._all_reduce(b.flat)
         else:
             b.work = self._all_reduce(b.flat)
 
@@ -201,6 +218,9 @@ class DataParallel(torch.nn.Module):
             if b.work is not None:
                 b.work.wait()  # compute stream waits for the NCCL stream
                 b.work = None
+            if b.done is not None:
+                torch.cuda.current_stream().wait_event(b.done)
+                b.done = None
         for p, (b, view) in self._slots.items():
             if p in b.ready:
                 p.grad = view

@@ -1,6 +1,8 @@
 """Thin tensor-level wrappers over the C ABI (include/b200vit.h).  Every function allocates its outputs with
 torch (caching allocator), passes raw device pointers + torch's current stream, and raises on any error.
 No op here has a PyTorch/CPU fallback: a missing library or a non-sm_100 device is an error."""
+import os
+
 import torch
 
 from . import _cabi
@@ -91,11 +93,22 @@ def gemm_bias(x, w, bias=None):
     return y
 
 
-def gemm_bias_gelu(x, w, bias=None):
-    """g = GELU(x w^T + bias) and gprime = GELU'(x w^T + bias), both bf16 (gprime is what backward needs)."""
+GELU_GRAD_Q8 = os.environ.get("B200VIT_GELU_GRAD_BF16", "0") != "1"   # B200VIT_GELU_GRAD_BF16=1: keep GELU' in bf16
+
+
+def gemm_bias_gelu(x, w, bias=None, q8=None):
+    """g = GELU(x w^T + bias) (bf16) and gprime = GELU'(x w^T + bias) -- what backward needs instead of the pre-activation.
+    gprime is the 8-bit fixed-point code of csrc/gemm_tcgen05.cuh (uint8; absolute error <= 0.0025 on a value in
+    [-0.13, 1.13]) whenever the 256-wide tile kernel applies (N a multiple of 256, more than 64 rows), bf16 otherwise."""
     M, K = x.shape
     N = w.shape[0]
+    if q8 is None:
+        q8 = GELU_GRAD_Q8 and N % 256 == 0 and M > 64
     g = torch.empty(M, N, device=x.device, dtype=BF16)
+    if q8:
+        gp = torch.empty(M, N, device=x.device, dtype=torch.uint8)
+        _call("b200vit_gemm_bias_gelu_q8", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(g), ptr(gp), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
+        return g, gp
     gp = torch.empty(M, N, device=x.device, dtype=BF16)
     _call("b200vit_gemm_bias_gelu", x, ptr(_chk(x, BF16, "x")), ptr(_chk(w, BF16, "w")), ptr(bias), ptr(g), ptr(gp), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
     return g, gp
@@ -161,6 +174,9 @@ def gemm_dgrad_dgelu(dy, w, gprime):
     M, N = dy.shape
     K = w.shape[1]
     dx = torch.empty(M, K, device=dy.device, dtype=BF16)
+    if u.dtype == torch.uint8:      # the 8-bit code written by gemm_bias_gelu(q8=True)
+        _call("b200vit_gemm_dgrad_dgelu_q8", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(w, BF16, "w")), ptr(_chk(u, torch.uint8, "u")), ptr(dx), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
+        return dx
     _call("b200vit_gemm_dgrad_dgelu", dy, ptr(_chk(dy, BF16, "dy")), ptr(_chk(w, BF16, "w")), ptr(_chk(u, BF16, "u")), ptr(dx), M, N, K, stream_ptr(), flops=2.0 * M * N * K)
     return dx
 
@@ -268,10 +284,13 @@ def cast_bf16(t, out=None):
     t = _chk(t, F32, "t")
     if out is None:
         out = torch.empty(t.shape, device=t.device, dtype=BF16)
-    if t.numel() % 4 == 0:
-        _call("b200vit_cast_f32_bf16", t, ptr(t), ptr(out), t.numel(), stream_ptr())
-    else:
-        out.copy_(t)
+    _call("b200vit_cast_f32_bf16", t, ptr(t), ptr(out), t.numel(), stream_ptr())     # any length: vector body + scalar tail
+    return out
+
+
+def cast_f32_from_bf16(t, out, scale=1.0):
+    """out (fp32, contiguous) <- scale * t (bf16, contiguous)."""
+    _call("b200vit_cast_bf16_f32", t, ptr(_chk(t, BF16, "t")), ptr(_chk(out, F32, "out")), t.numel(), float(scale), stream_ptr())
     return out
 
 

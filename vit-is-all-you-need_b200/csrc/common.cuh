@@ -343,6 +343,9 @@ int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
                      uint32_t box_rows, uint32_t box_cols);
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, bool f32);
+// 2-D uint8 row-major tensor, 128-byte swizzle (box_cols <= 128)
+int make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols);
 // Generic N-D bf16 map (dims/strides innermost first; strides in BYTES for dims 1..rank-1).
 int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                       const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);

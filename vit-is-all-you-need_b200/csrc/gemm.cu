@@ -60,6 +60,10 @@ static int launch(const void* A, long long lda, const void* B, long long ldb, in
       rc = make_tmap_2d_bf16(&to2, out2, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo, 32, 64);
       if (rc != OK) return rc;
     }
+    if (KIND == EPI_GELU_Q8) {
+      rc = make_tmap_2d_u8(&to2, out2, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldo, 32, 128);
+      if (rc != OK) return rc;
+    }
   }
 
   auto kern = gemm_tcgen05_kernel<A_MN, B_MN, BN, KIND, NCTA>;
@@ -228,6 +232,33 @@ int b200vit_gemm_dgrad_dgelu(const void* dy, const void* w, const void* gprime, 
   ep.aux = gprime; ep.ldaux = K;
   return launch_bn<false, true, EPI_MUL_BF16>(dy, N, w, K, M, K, N, ep, false, (cudaStream_t)stream);
 }
+
+// The same two GEMMs with GELU'(u) carried as the 8-bit code of gemm_tcgen05.cuh (GP_LO / GP_STEP): half the bytes for the
+// tensor that bounds both kernels.  256-wide tiles only (the u8 staging slab holds a warp's 128 columns).
+int b200vit_gemm_bias_gelu_q8(const void* x, const void* w, const float* bias, void* g, void* gprime_q8, int M, int N, int K,
+                              void* stream) {
+  int rc = check_common(x, w, g, M, N, K);
+  if (rc) return rc;
+  B200_REQUIRE(gprime_q8 != nullptr && N % 16 == 0, "gemm_bias_gelu_q8: gprime is null or N=%d is not a multiple of 16", N);
+  EpiParams ep = make_ep(g, N);
+  ep.bias = bias;
+  if (M > GEMM_BM) return launch<false, false, 256, EPI_GELU_Q8, 2>(x, K, w, K, M, N, K, ep, gprime_q8, false, (cudaStream_t)stream);
+  return launch<false, false, 256, EPI_GELU_Q8, 1>(x, K, w, K, M, N, K, ep, gprime_q8, false, (cudaStream_t)stream);
+}
+
+int b200vit_gemm_dgrad_dgelu_q8(const void* dy, const void* w, const void* gprime_q8, void* dx, int M, int N, int K,
+                                void* stream) {
+  int rc = check_common(dy, w, dx, M, N, K);
+  if (rc) return rc;
+  B200_REQUIRE(gprime_q8 != nullptr && K % 16 == 0, "gemm_dgrad_dgelu_q8: gprime is null or K=%d is not a multiple of 16", K);
+  EpiParams ep = make_ep(dx, K);
+  ep.aux = gprime_q8; ep.ldaux = K;
+  if (M > GEMM_BM) return launch<false, true, 256, EPI_MUL_Q8, 2>(dy, N, w, K, M, K, N, ep, nullptr, false, (cudaStream_t)stream);
+  return launch<false, true, 256, EPI_MUL_Q8, 1>(dy, N, w, K, M, K, N, ep, nullptr, false, (cudaStream_t)stream);
+}
+
+float b200vit_gelu_grad_code_lo(void) { return GP_LO; }
+float b200vit_gelu_grad_code_step(void) { return GP_STEP; }
 
 // dw[N,K] = dy[M,N]^T x[M,K]: output rows = N, output cols = K, contraction over M (split-K).
 // db[N] (optional) = column sums of dy, accumulated by two otherwise idle warps from the smem dy tiles.

@@ -59,7 +59,33 @@ enum EpiKind : int {
   EPI_DROP_RESID_F32 = 7,  // out(f32) = aux(f32) + dropout(acc + bias)   (mlp[2] + nn.Dropout + residual)
   EPI_DEPATCH_F32 = 8,     // de-patchify: out(f32)[b, c, h*p + p1, w*p + p2] = acc + bias for row = b*P + h*Wt + w and
                            // column = c*p*p + p1*p + p2 (weight rows pre-permuted to channel-major), direct stores
+  EPI_GELU_Q8 = 9,         // as EPI_GELU_BF16 with out2(u8) = the 8-bit code of gelu'(u) (gelu_grad_code): half the bytes
+  EPI_MUL_Q8 = 10,         // as EPI_MUL_BF16 with aux(u8) = that code
 };
+
+// 8-bit fixed-point code of GELU'(u): the derivative lives in [-0.1290, 1.1290] whatever u is, so a uniform grid over
+// [GP_LO, GP_LO + 255 GP_STEP] has an absolute error <= GP_STEP / 2 = 0.0025 (rms 0.0014) -- against values of order
+// 0.5..1 that is the size of the bf16 rounding of the product it enters (dy W) * gelu'(u), which is rounded to bf16 anyway.
+// The fc1+GELU GEMM and its backward twin are bounded by HBM bytes of exactly this tensor, so the code
+// halves what they move for it.
+constexpr float GP_STEP = 1.27f / 255.0f;
+constexpr float GP_OFF = 27.0f;                 // an INTEGER offset: 2^23 + GP_OFF is exact, so one FMA rounds to the code
+constexpr float GP_LO = -GP_OFF * GP_STEP;      // -0.13447; the grid ends at GP_LO + 255 GP_STEP = 1.13553
+__device__ __forceinline__ uint32_t gelu_grad_code_bits(float gp) {   // code in the low byte of the result
+  return __float_as_uint(fmaf(gp, 1.0f / GP_STEP, GP_OFF + 8388608.0f));
+}
+__device__ __forceinline__ uint32_t pack_codes4(float a, float b, float c, float d) {
+  const uint32_t lo = __byte_perm(gelu_grad_code_bits(a), gelu_grad_code_bits(b), 0x0040);
+  const uint32_t hi = __byte_perm(gelu_grad_code_bits(c), gelu_grad_code_bits(d), 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
+}
+__device__ __forceinline__ float gelu_grad_decode(uint32_t word, int byte) {   // byte 0..3 of word
+  const float f = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 + byte)) - 8388608.0f;   // exact integer 0..255
+  return fmaf(f, GP_STEP, GP_LO);
+}
+
+__host__ __device__ constexpr bool epi_is_gelu(int kind) { return kind == EPI_GELU_BF16 || kind == EPI_GELU_Q8; }
+__host__ __device__ constexpr bool epi_is_mul(int kind) { return kind == EPI_MUL_BF16 || kind == EPI_MUL_Q8; }
 
 __host__ __device__ constexpr bool epi_direct_stores(int kind) { return kind == EPI_PATCH_F32 || kind == EPI_DEPATCH_F32; }
 
@@ -170,7 +196,8 @@ struct GemmCfg {
   static constexpr int B_ROWS = BN / NCTA;               // B-tile rows staged by this CTA
   static constexpr int B_BYTES = B_ROWS * GEMM_BK * 2;   // 1 CTA: 32 KB (BN=256) / 16 KB (BN=128); CTA pair: half
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SLABS = (KIND == EPI_GELU_BF16) ? 2 : 1;  // staging slabs (32 rows x 128 B) per epilogue warp
+  static constexpr int SLABS = epi_is_gelu(KIND) ? 2 : 1;  // staging slabs (32 rows x 128 B) per epilogue warp
+  static_assert(KIND != EPI_GELU_Q8 || BN == 256, "the u8 slab holds the warp's 128 columns of a 256-wide tile");
   static constexpr int EPI_BYTES = GEMM_EPI_WARPS * SLABS * 4096;
   static constexpr int STAGES = (200 * 1024 + 28 * 1024 - EPI_BYTES) / STAGE_BYTES > 6
                                     ? 6 : (200 * 1024 + 28 * 1024 - EPI_BYTES) / STAGE_BYTES;
@@ -232,7 +259,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (!epi_direct_stores(KIND)) tma_prefetch_desc(&tma_out);
-    if (KIND == EPI_GELU_BF16) tma_prefetch_desc(&tma_out2);
+    if (epi_is_gelu(KIND)) tma_prefetch_desc(&tma_out2);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], (NCTA == 2 && leader) ? 2 : 1);  // own producer (+ the peer's relay)
       mbar_init(&empty_bar[i], do_colsum ? 3 : 1);  // MMA commit (+ the two column-sum warps)
@@ -426,12 +453,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint4 auxq[2][4];
       auto load_aux = [&](int c, uint4 (&dst)[4]) {
         const int col = n0 + c * 32;
-        const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)row * ep.ldaux + col;
+        if constexpr (KIND == EPI_MUL_Q8) {   // 32 one-byte codes per row and chunk
+          const uint8_t* a = reinterpret_cast<const uint8_t*>(ep.aux) + (long long)row * ep.ldaux + col;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = (row_ok && col + q * 8 < s.N) ? __ldg(reinterpret_cast<const uint4*>(a) + q) : make_uint4(0, 0, 0, 0);
+          for (int q = 0; q < 2; ++q)
+            dst[q] = (row_ok && col + q * 16 < s.N) ? __ldg(reinterpret_cast<const uint4*>(a) + q) : make_uint4(0, 0, 0, 0);
+        } else {
+          const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(ep.aux) + (long long)row * ep.ldaux + col;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = (row_ok && col + q * 8 < s.N) ? __ldg(reinterpret_cast<const uint4*>(a) + q) : make_uint4(0, 0, 0, 0);
+        }
       };
-      if constexpr (KIND == EPI_MUL_BF16) load_aux(0, auxq[0]);
+      if constexpr (epi_is_mul(KIND)) load_aux(0, auxq[0]);
       mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BN + half * (BN / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -441,7 +475,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       for (int c = 0; c < NCH; ++c) {
         tmem_ld_wait();
         if (c + 1 < NCH) tmem_ld32(taddr + (c + 1) * 32, vbuf[(c + 1) & 1]);
-        if constexpr (KIND == EPI_MUL_BF16) {
+        if constexpr (epi_is_mul(KIND)) {
           if (c + 1 < NCH) load_aux(c + 1, auxq[(c + 1) & 1]);
         }
         const int col = n0 + c * 32;
@@ -449,7 +483,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vbuf[c & 1][j]);
-          if constexpr (KIND == EPI_BF16 || KIND == EPI_GELU_BF16 || KIND == EPI_RESID_F32 || KIND == EPI_F32 ||
+          if constexpr (KIND == EPI_BF16 || epi_is_gelu(KIND) || KIND == EPI_RESID_F32 || KIND == EPI_F32 ||
                         KIND == EPI_PATCH_F32 || KIND == EPI_DROP_RESID_F32 || KIND == EPI_DEPATCH_F32) {
             if (ep.bias != nullptr) {
 #pragma unroll
@@ -543,8 +577,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 v[q * 8 + 4] *= a2.x; v[q * 8 + 5] *= a2.y; v[q * 8 + 6] *= a3.x; v[q * 8 + 7] *= a3.y;
               }
             }
+            if constexpr (KIND == EPI_MUL_Q8) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const uint4 uu = auxq[c & 1][q];
+                const uint32_t wd[4] = {uu.x, uu.y, uu.z, uu.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                  for (int b = 0; b < 4; ++b) v[q * 16 + i * 4 + b] *= gelu_grad_decode(wd[i], b);
+                }
+              }
+            }
             float gp[32];
-            if constexpr (KIND == EPI_GELU_BF16) {
+            if constexpr (epi_is_gelu(KIND)) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) gelu_and_grad(v[j], v[j], gp[j]);
             }
@@ -563,6 +609,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                                pack_bf16(gp[q * 8 + 4], gp[q * 8 + 5]), pack_bf16(gp[q * 8 + 6], gp[q * 8 + 7]));
               }
             }
+            if constexpr (KIND == EPI_GELU_Q8) {
+              // one-byte codes: the u8 slab row (128 B) holds all 4 chunks of this warp; 32 codes = two 16-byte pieces.
+              // (the wait at c == 0 above also covered the previous tile's store of this slab)
+#pragma unroll
+              for (int q = 0; q < 2; ++q)
+                *slab_chunk(slab1, lane, c * 2 + q) =
+                    make_uint4(pack_codes4(gp[q * 16 + 0], gp[q * 16 + 1], gp[q * 16 + 2], gp[q * 16 + 3]),
+                               pack_codes4(gp[q * 16 + 4], gp[q * 16 + 5], gp[q * 16 + 6], gp[q * 16 + 7]),
+                               pack_codes4(gp[q * 16 + 8], gp[q * 16 + 9], gp[q * 16 + 10], gp[q * 16 + 11]),
+                               pack_codes4(gp[q * 16 + 12], gp[q * 16 + 13], gp[q * 16 + 14], gp[q * 16 + 15]));
+            }
             if ((c & 1) == 1 || c == NCH - 1 || col + 32 >= s.N) {
               fence_proxy_async_smem();
               __syncwarp();
@@ -570,6 +627,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
                 const int c0 = n0 + (c & ~1) * 32;
                 tma_store_2d(&tma_out, slab0, c0, m0);
                 if constexpr (KIND == EPI_GELU_BF16) tma_store_2d(&tma_out2, slab1, c0, m0);
+                if constexpr (KIND == EPI_GELU_Q8) {
+                  if (c == NCH - 1 || col + 32 >= s.N) tma_store_2d(&tma_out2, slab1, n0, m0);
+                }
                 tma_store_commit();
               }
             }

@@ -151,13 +151,26 @@ __global__ void colsum_f32_kernel(const float* __restrict__ a, float* __restrict
   out[c] = s;
 }
 
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+// n = 4 * n4 + tail elements: vector body plus a scalar tail (any length; the base pointers are 16-byte aligned)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4, int tail) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(in)[i];
     uint2 w;
     w.x = pack_bf16(v.x, v.y); w.y = pack_bf16(v.z, v.w);
     reinterpret_cast<uint2*>(out)[i] = w;
   }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) out[n4 * 4 + threadIdx.x] = __float2bfloat16_rn(in[n4 * 4 + threadIdx.x]);
+}
+
+// out(f32) = scale * in(bf16): gradients coming back from a bf16-compressed all-reduce (ddp.py)
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n4, int tail,
+                                     float scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint2 u = reinterpret_cast<const uint2*>(in)[i];
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+    reinterpret_cast<float4*>(out)[i] = make_float4(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < tail) out[n4 * 4 + threadIdx.x] = __bfloat162float(in[n4 * 4 + threadIdx.x]) * scale;
 }
 
 static int grid_for(long long work, int threads) {
@@ -175,8 +188,17 @@ using namespace b200;
 extern "C" {
 
 int b200vit_cast_f32_bf16(const float* in, void* out, long long n, void* stream) {
-  B200_REQUIRE(in && out && n > 0 && n % 4 == 0, "cast_f32_bf16: n=%lld must be a positive multiple of 4", n);
-  cast_f32_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n / 4);
+  B200_REQUIRE(in && out && n > 0, "cast_f32_bf16: bad arguments (n=%lld)", n);
+  B200_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 7) == 0, "cast_f32_bf16: pointers must be 16- / 8-byte aligned");
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n / 4, (int)(n % 4));
+  B200_CUDA(cudaGetLastError());
+  return OK;
+}
+
+int b200vit_cast_bf16_f32(const void* in, float* out, long long n, float scale, void* stream) {
+  B200_REQUIRE(in && out && n > 0, "cast_bf16_f32: bad arguments (n=%lld)", n);
+  B200_REQUIRE(((uintptr_t)out & 15) == 0 && ((uintptr_t)in & 7) == 0, "cast_bf16_f32: pointers must be 16- / 8-byte aligned");
+  cast_bf16_f32_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, out, n / 4, (int)(n % 4), scale);
   B200_CUDA(cudaGetLastError());
   return OK;
 }

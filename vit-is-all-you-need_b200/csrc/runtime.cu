@@ -55,8 +55,25 @@ static int load_encode() {
   return OK;
 }
 
+static int make_tmap_nd_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                              const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, CUtensorMapDataType dtype);
+
 int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, bool f32) {
+  return make_tmap_nd_typed(out, base, rank, dims, strides_bytes, box, swizzle128,
+                            f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+
+int make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows, uint32_t box_cols) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[2] = {1, ld};
+  const uint32_t box[2] = {box_cols, box_rows};
+  return make_tmap_nd_typed(out, base, 2, dims, strides, box, true, CU_TENSOR_MAP_DATA_TYPE_UINT8);
+}
+
+static int make_tmap_nd_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                              const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, CUtensorMapDataType dtype) {
   int rc = load_encode();
   if (rc != OK) return rc;
   cuuint64_t gdim[5];
@@ -80,7 +97,7 @@ int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* d
       return ERR_ARG;
     }
   }
-  CUresult r = g_encode(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+  CUresult r = g_encode(out, dtype, (cuuint32_t)rank,
                         const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
