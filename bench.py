@@ -308,7 +308,9 @@ def run_gpu_arm(args):
 
     B = args.batch
     model = build_model(torch, M, device, args.dropout)
-    wrapped = b200_ddp.DataParallel(model, bucket_mb=args.bucket_mb) if world > 1 else model
+    bucket_mb = args.bucket_mb if args.bucket_mb > 0 else 1e9
+    wrapped = (b200_ddp.DataParallel(model, bucket_mb=bucket_mb, compress_bf16=(args.grad_compress == "bf16"))
+               if world > 1 else model)
     from b200vit import optim as b200_optim
     if args.optimizer == "torch-fused":
         optim = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2, fused=True)
@@ -429,6 +431,8 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "ViT-B/16 224px ImageNet-shape train step (fwd + CE + bwd + AdamW), configs[1]",
                    "per_gpu_batch": B, "global_batch": B * world, "seq_len": NTOK, "parallelism": f"dp{world}", "dropout": args.dropout,
+                   "grad_exchange": None if world == 1 else (("one bucket reduced after backward" if args.bucket_mb <= 0 else f"{args.bucket_mb:g} MB buckets overlapped with backward")
+                                                             + (", bf16-compressed NCCL all-reduce" if args.grad_compress == "bf16" else ", fp32 NCCL all-reduce")),
                    "optimizer": "torch.optim.AdamW(fused=True)" if args.optimizer == "torch-fused" else "b200vit.optim.AdamW (fused multi-tensor + bf16 operand refresh)", "l2": "per-step working set >> 126 MB L2 (no flush needed)",
                    "train_gflop_per_image": train_flops_per_image() / 1e9},
         "e2e": {"value": ips_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -478,7 +482,14 @@ def main():
     ap.add_argument("--workload", type=str, default="vit_b", choices=["vit_b", "vit_l", "vit_ti", "titok_s", "tatitok_s", "videogpt_b", "vq"],
                     help="vit_b (default) = BASELINE.json configs[1], the headline; the others are the remaining configs through the "
                          "same JSON contract (bench_workloads.py)")
-    ap.add_argument("--bucket-mb", type=float, default=32.0)
+    ap.add_argument("--bucket-mb", type=float, default=0.0,
+                    help="gradient bucket size for N > 1; 0 (default) = ONE bucket reduced right after backward.  Measured at 8 GPUs "
+                         "(profiles/r2_ddp_8gpu_ab.md): overlapped 32 MB buckets 31.98 ms/step, one deferred bucket 30.99 (fp32) / "
+                         "30.73 (bf16): NCCL's CTAs cannot share an SM with the persistent GEMM CTAs (the GEMM owns the whole register "
+                         "file), so every overlapped bucket displaces GEMM CTAs of a statically partitioned grid")
+    ap.add_argument("--grad-compress", type=str, default="bf16", choices=["none", "bf16"],
+                    help="bf16: the bucket crosses NVLink as bf16 (cast - all-reduce(avg) - cast back into the fp32 bucket), like "
+                         "torch's bf16_compress_hook; none: fp32 all-reduce")
     ap.add_argument("--impl", type=str, default="b200vit", choices=["b200vit", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU-baseline sample (a few seconds per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -225,7 +225,8 @@ def run(args):
     torch.manual_seed(0)
     model, loss_fn = w["ours"]()
     model = model.to(device)
-    wrapped = b200_ddp.DataParallel(model, bucket_mb=args.bucket_mb) if world > 1 else model
+    wrapped = (b200_ddp.DataParallel(model, bucket_mb=args.bucket_mb if args.bucket_mb > 0 else 1e9,
+                                     compress_bf16=(args.grad_compress == "bf16")) if world > 1 else model)
     use_graph = bool(w.get("graph")) and world == 1
     optim = b200_optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2, capturable=use_graph)
     step = _train_step_factory(torch, wrapped, loss_fn, optim)
