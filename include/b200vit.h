@@ -30,6 +30,7 @@ int b200vit_version(void);
 const char* b200vit_last_error(void);
 int b200vit_debug_set(int key, int value); /* bring-up knobs (descriptor sweeps); not for production */
 int b200vit_debug_max_clusters(void);      /* bring-up aid: co-resident CTA pairs of the GEMM kernel */
+int b200vit_debug_tmap_cache_stats(unsigned long long* hits_misses); /* TMA descriptor cache: out[0] hits, out[1] misses */
 
 /* ---- dense contractions: bf16 operands, fp32 accumulation in TMEM (tcgen05) --------------------- */
 /* y[M,N](bf16) = x[M,K] w[N,K]^T + bias[N]            nn.Linear forward, transformer.py:21,27 (qkv)   */

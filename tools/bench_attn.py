@@ -39,9 +39,21 @@ print(f"attn bwd  B={B} N={N} H={H}: {t:8.1f} us  {2.5*fl/t/1e6:7.1f} TFLOP/s (2
 if "--attn-only" in sys.argv:
     sys.exit(0)
 if "--sdpa" in sys.argv:
-    q, k, v = (qkv.view(B, N, 3, H, 64)[:, :, i].transpose(1, 2) for i in range(3))
-    t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
+    # the same-box library comparator: F.scaled_dot_product_attention exactly as transformer.py:27-28 calls it (strided q/k/v views
+    # of the fused projection, additive -inf mask when causal), forward and backward
+    q, k, v = (qkv.view(B, N, 3, H, 64)[:, :, i].transpose(1, 2).detach().requires_grad_(True) for i in range(3))
+    mask = None
+    if causal:
+        mask = torch.triu(torch.ones(N, N, device=dev), diagonal=1)
+        mask = mask.masked_fill(mask == 1, float("-inf")).to(torch.bfloat16)
+    sd = lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask)  # noqa: E731
+    t = timeit(sd)
     print(f"torch SDPA fwd: {t:8.1f} us  {fl/t/1e6:7.1f} TFLOP/s")
+    out = sd()
+    go = do.view(B, N, H, 64).transpose(1, 2)
+    tb = timeit(lambda: torch.autograd.grad(out, (q, k, v), go, retain_graph=True))
+    print(f"torch SDPA bwd: {tb:8.1f} us  {2.5*fl/tb/1e6:7.1f} TFLOP/s")
+    sys.exit(0)
 M = B * N
 x = torch.randn(M, d, device=dev)
 add = torch.randn(M, d, device=dev).to(torch.bfloat16)

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "b200vit_version": (_I, []),
     "b200vit_debug_set": (_I, [_I, _I]),
     "b200vit_debug_max_clusters": (_I, []),
+    "b200vit_debug_tmap_cache_stats": (_I, [_P]),
     "b200vit_gemm_bias": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "b200vit_gemm_bias_gelu": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "b200vit_gemm_bias_gelu_q8": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),

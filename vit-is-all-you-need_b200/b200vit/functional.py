@@ -71,7 +71,7 @@ def invalidate_weight_cache(module_or_params=None):
         return
     params = module_or_params.parameters() if hasattr(module_or_params, "parameters") else module_or_params
     for p in params:
-        for attr in ("_b200_bf16", "_b200_folded"):
+        for attr in ("_b200_bf16", "_b200_folded", "_b200_depatch"):
             if hasattr(p, attr):
                 delattr(p, attr)
 
@@ -456,6 +456,22 @@ def _depatch_perm(C, p, device):
     return _DEPATCH_PERM[key]
 
 
+def _depatch_operands(weight, bias, Cpp, d, perm):
+    """Channel-major bf16 weight / fp32 bias of the de-patchify GEMM, cached on the weight until an optimizer steps or the
+    parameters change (the (p1 p2 c) -> (c p1 p2) row permutation used to run as two index_select kernels per forward)."""
+    key = (_STEP_EPOCH, weight._version, weight.data_ptr(), None if bias is None else (bias._version, bias.data_ptr()))
+    cached = getattr(weight, "_b200_depatch", None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    w_c = bf16_of(weight).view(Cpp, d).index_select(0, perm)
+    b_c = None if bias is None else _f32c(bias).index_select(0, perm)
+    try:
+        weight._b200_depatch = (key, w_c, b_c)
+    except Exception:  # pragma: no cover
+        pass
+    return w_c, b_c
+
+
 class DepatchifyFn(torch.autograd.Function):
     """De-patchify tail of the tokenizer decoders (train_titok.py:67,71-74): tokens[:, :P] -> 'b (h w) c -> b c h w' ->
     Conv2d(d, C*p*p, 1) -> 'b (p1 p2 c) h w -> b c (h p1) (w p2)', as ONE tcgen05 GEMM over the gathered bf16 token rows
@@ -471,8 +487,7 @@ class DepatchifyFn(torch.autograd.Function):
         P = Ht * Wt
         perm, inv = _depatch_perm(C, p, tokens.device)
         rows = ops.gather_tokens_bf16(_as_rows_f32(tokens), 0, P)
-        w_c = bf16_of(weight).view(Cpp, d).index_select(0, perm)
-        b_c = None if bias is None else _f32c(bias).index_select(0, perm)
+        w_c, b_c = _depatch_operands(weight, bias, Cpp, d, perm)
         img = ops.depatchify_fwd(rows, w_c, b_c, B, Ht, Wt, p, C)
         ctx.saved = (rows, w_c, inv)
         ctx.dims = (B, N, d, C, P, p, tuple(weight.shape))

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "../../include/b200vit.h"
 #include "common.cuh"
 
@@ -72,8 +75,58 @@ int make_tmap_2d_u8(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
   return make_tmap_nd_typed(out, base, 2, dims, strides, box, true, CU_TENSOR_MAP_DATA_TYPE_UINT8);
 }
 
+// Encoded tensor maps are pure functions of (address, shape, strides, box, type, swizzle): cache them.  A GEMM launch needs
+// 3-4 maps and cuTensorMapEncodeTiled costs ~1-2 us of host time each, which is what made the launch-bound configurations
+// (ViT-Ti, single-token decode) need a CUDA graph; PyTorch's caching allocator hands the same addresses back step after step,
+// so the hit rate in a training loop is ~100 %.  Forward runs on the Python main thread, backward on autograd's device
+// thread: one mutex.  The cache is bounded (cleared when full) and holds no ownership of the memory it describes.
+struct TmapKey {
+  uint64_t w[13];
+  bool operator==(const TmapKey& o) const { return memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : k.w) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); }
+    return (size_t)h;
+  }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static unsigned long long g_tmap_hits = 0, g_tmap_misses = 0;
+
+static int encode_tmap_nd_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, CUtensorMapDataType dtype);
+
 static int make_tmap_nd_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                               const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, CUtensorMapDataType dtype) {
+  if (rank < 1 || rank > 5) { set_error("tensor map rank %d out of range", rank); return ERR_ARG; }
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.w[0] = (uint64_t)reinterpret_cast<uintptr_t>(base);
+  key.w[1] = (uint64_t)rank | ((uint64_t)dtype << 8) | ((uint64_t)(swizzle128 ? 1 : 0) << 32);
+  for (int i = 0; i < rank; ++i) {
+    key.w[2 + i] = dims[i];
+    key.w[7 + i] = (i > 0 ? strides_bytes[i] : 0) ^ ((uint64_t)box[i] << 48);
+  }
+  if (g_debug[11] != 1) {   // knob 11 = 1: bypass the cache (A/B)
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *out = it->second; ++g_tmap_hits; return OK; }
+  }
+  int rc = encode_tmap_nd_typed(out, base, rank, dims, strides_bytes, box, swizzle128, dtype);
+  if (rc != OK) return rc;
+  if (g_debug[11] != 1) {
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
+    ++g_tmap_misses;
+  }
+  return OK;
+}
+
+static int encode_tmap_nd_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, CUtensorMapDataType dtype) {
   int rc = load_encode();
   if (rc != OK) return rc;
   cuuint64_t gdim[5];
@@ -150,6 +203,14 @@ int b200vit_init(int device) {
   }
   b200::g_num_sms = prop.multiProcessorCount;
   return b200::load_encode();
+}
+
+/* bring-up aid: tensor-map cache statistics (hits in out[0], misses in out[1]) */
+int b200vit_debug_tmap_cache_stats(unsigned long long* out) {
+  if (out == nullptr) return b200::ERR_ARG;
+  std::lock_guard<std::mutex> lock(b200::g_tmap_mu);
+  out[0] = b200::g_tmap_hits; out[1] = b200::g_tmap_misses;
+  return b200::OK;
 }
 
 int b200vit_debug_set(int key, int value) {

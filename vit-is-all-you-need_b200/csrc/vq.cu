@@ -52,9 +52,11 @@ __global__ void vq_prep_kernel(const float* __restrict__ codebook, int K, int D,
 
 constexpr int VQ_THREADS = 256;
 constexpr int VQ_WARPS = VQ_THREADS / 32;
+constexpr int VQ_MAX_WARPS = 16;
 
-template <int DP, int ROWS>
-__global__ void __launch_bounds__(VQ_THREADS, 1)
+// MAXT = largest block the instantiation is launched with (register cap); the block size itself is a launch parameter
+template <int DP, int ROWS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 vq_fwd_kernel(const float* __restrict__ x, const float* __restrict__ codebook,
               const float* __restrict__ ehat, const float* __restrict__ ee, VqLayout L, int KC,
               long long* __restrict__ idx_out, float* __restrict__ q_out, double* __restrict__ partial) {
@@ -62,10 +64,11 @@ vq_fwd_kernel(const float* __restrict__ x, const float* __restrict__ codebook,
   float* s_codes = reinterpret_cast<float*>(vq_smem4);
   constexpr int STRIDE = (DP % 8 == 4) ? DP : DP + 4;
   float* s_ee = s_codes + (size_t)KC * STRIDE;
-  __shared__ double s_part[VQ_WARPS];
+  __shared__ double s_part[VQ_MAX_WARPS];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row0 = ((long long)blockIdx.x * VQ_WARPS + warp) * ROWS;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const long long row0 = ((long long)blockIdx.x * nwarps + warp) * ROWS;
   const bool l2 = (L.flags & 1) != 0;
   const bool gather_norm = (L.flags & 2) != 0;
 
@@ -105,12 +108,12 @@ vq_fwd_kernel(const float* __restrict__ x, const float* __restrict__ codebook,
     const int kc = min(KC, L.K - k0);
     __syncthreads();  // previous chunk fully consumed
     // stage the chunk: 16-byte copies, padded row stride
-    for (int i = threadIdx.x; i < kc * (DP / 4); i += VQ_THREADS) {
+    for (int i = threadIdx.x; i < kc * (DP / 4); i += nthreads) {
       const int k = i / (DP / 4), v = i - k * (DP / 4);
       const float4 t = __ldg(reinterpret_cast<const float4*>(ehat + (long long)(k0 + k) * DP) + v);
       *reinterpret_cast<float4*>(s_codes + (size_t)k * STRIDE + v * 4) = t;
     }
-    for (int i = threadIdx.x; i < kc; i += VQ_THREADS) s_ee[i] = __ldg(ee + k0 + i);
+    for (int i = threadIdx.x; i < kc; i += nthreads) s_ee[i] = __ldg(ee + k0 + i);
     __syncthreads();
 
     for (int k = lane; k < kc; k += 32) {
@@ -172,7 +175,7 @@ vq_fwd_kernel(const float* __restrict__ x, const float* __restrict__ codebook,
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < VQ_WARPS; ++w) t += s_part[w];
+    for (int w = 0; w < nwarps; ++w) t += s_part[w];
     partial[blockIdx.x] = t;
   }
 }
@@ -240,10 +243,10 @@ static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static int vq_rows_per_cta(int DP) { return VQ_WARPS * (DP <= 16 ? 4 : (DP <= 32 ? 2 : 1)); }
 
-template <int DP, int ROWS>
+template <int DP, int ROWS, int MAXT = VQ_THREADS>
 static int launch_vq_fwd(const float* x, const float* codebook, const float* ehat, const float* ee,
                          const VqLayout& L, long long* idx, float* q, double* partial, int grid,
-                         cudaStream_t st) {
+                         cudaStream_t st, int threads = VQ_THREADS) {
   constexpr int STRIDE = (DP % 8 == 4) ? DP : DP + 4;
   const size_t per_code = (size_t)STRIDE * 4 + 4;
   // 4096 codes x (12 floats + norm) = 213 KB: the whole TiTok codebook in ONE chunk (a 200 KB budget split it into
@@ -253,9 +256,9 @@ static int launch_vq_fwd(const float* x, const float* codebook, const float* eha
   if (KC > L.K) KC = L.K;
   KC = (KC + 3) & ~3;  // keep s_ee 16-byte aligned after the code rows
   const size_t smem = (size_t)KC * per_code + 16;
-  auto kern = vq_fwd_kernel<DP, ROWS>;
+  auto kern = vq_fwd_kernel<DP, ROWS, MAXT>;
   B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-  kern<<<grid, VQ_THREADS, smem, st>>>(x, codebook, ehat, ee, L, KC, idx, q, partial);
+  kern<<<grid, threads, smem, st>>>(x, codebook, ehat, ee, L, KC, idx, q, partial);
   B200_CUDA(cudaGetLastError());
   return OK;
 }
@@ -268,7 +271,8 @@ extern "C" {
 
 size_t b200vit_vq_workspace_size(long long R, int D, int K) {
   const int DP = vq_dp(D);
-  const long long grid = (R + vq_rows_per_cta(DP) - 1) / vq_rows_per_cta(DP);
+  const int rpc_min = DP <= 16 ? 16 : vq_rows_per_cta(DP);   // the many-warp variant may use as few as 4 warps x 4 rows per CTA
+  const long long grid = (R + rpc_min - 1) / rpc_min;
   return align256((size_t)K * DP * 4) + align256((size_t)K * 4) + align256((size_t)grid * 8);
 }
 
@@ -300,10 +304,35 @@ int b200vit_vq_fwd(const float* x, const float* codebook, long long R, int D, in
   // (K 2048, rows 65536: 166 -> 200 us), so it is not used there.  Same arithmetic per (row, code): bit-exact indices.
   const int stride = (DP % 8 == 4) ? DP : DP + 4;
   const bool one_cta_per_sm = (size_t)K * (stride * 4 + 4) > 113 * 1024;
-  const bool rows8 = DP <= 16 && DP >= 12 && one_cta_per_sm && (R + rpc - 1) / rpc > num_sms();
-  if (rows8) rpc *= 2;
+  // Round 2 (ncu: 2 warps per scheduler issue 0.47 instructions per clock, long-/short-scoreboard stalls, 128 of 148 SMs
+  // busy): when the codebook pins one CTA per SM, run up to 16 warps of 4 rows each -- 4 warps per scheduler hide the
+  // shared-memory and FMA-chain latencies -- and size the CTA (4..16 warps) so that one wave covers all SMs.  Same
+  // arithmetic per (row, code) in the same order: bit-exact indices.
+  const bool many_warps = (DP == 12 || DP == 16) && one_cta_per_sm;
+  int threads = VQ_THREADS;
+  bool rows8 = false;
+  if (many_warps) {
+    const long long per_wave = (long long)num_sms() * 4;                    // rows per wave with ONE warp per CTA
+    const long long waves16 = (R + per_wave * VQ_MAX_WARPS - 1) / (per_wave * VQ_MAX_WARPS);
+    long long w = (R + per_wave * waves16 - 1) / (per_wave * waves16);      // warps per CTA that fill the same number of waves
+    if (w < 4) w = 4;
+    if (w > VQ_MAX_WARPS) w = VQ_MAX_WARPS;
+    threads = (int)w * 32;
+    rpc = (int)w * 4;
+  } else {
+    rows8 = DP <= 16 && DP >= 12 && one_cta_per_sm && (R + rpc - 1) / rpc > num_sms();
+    if (rows8) rpc *= 2;
+  }
   const int grid = (int)((R + rpc - 1) / rpc);
   int rc;
+  if (many_warps) {
+    if (DP == 12) rc = launch_vq_fwd<12, 4, 512>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st, threads);
+    else          rc = launch_vq_fwd<16, 4, 512>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st, threads);
+    if (rc != OK) return rc;
+    vq_finalize_kernel<<<1, 32, 0, st>>>(partial, grid, (double)R * D, commitment_cost, losses);
+    B200_CUDA(cudaGetLastError());
+    return OK;
+  }
   switch (DP) {
     case 4:  rc = launch_vq_fwd<4, 4>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st); break;
     case 8:  rc = launch_vq_fwd<8, 4>(x, codebook, ehat, ee, L, indices, quantized, partial, grid, st); break;
