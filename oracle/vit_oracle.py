@@ -254,6 +254,105 @@ def residual_attention_block_bwd(dy_lnd, cache):
 
 
 # ------------------------------------------------------------------------------------------------
+# blocks.TiTokEncoder / TiTokDecoder (blocks.py:208-361): token-sequence assembly, ln_pre, ResidualAttentionBlock stack,
+# ln_post, conv_out (encoder) / ffn de-patchify (decoder; the final 3x3 conv_out of the decoder, blocks.py:334,361, is outside
+# the hot path and NOT restated: `blocks_titok_decoder_fwd` returns the image that enters it).
+# P: patch_w [d,3,p,p] patch_b cls [1,d] pos [1+G,d] latent_pos [L,d] ln_pre_w/b blocks [list of RAB dicts] ln_post_w/b
+#    encoder: conv_out_w [ts,d,1,1] conv_out_b ; decoder: embed_w [d,ts] embed_b mask [1,1,d] ffn_w [3pp,d,1,1] ffn_b
+# ------------------------------------------------------------------------------------------------
+def blocks_tokens_encoder(x, latent_tokens, P):
+    """blocks.py:257-267: [cls + pos[0] | patch_embed(x) + pos[1:] | latent_tokens + latent_pos] -> [B, 1 + G + L, d]."""
+    d, C, p, _ = P["patch_w"].shape
+    cols = im2col(x, p)
+    patches = cols @ P["patch_w"].reshape(d, C * p * p).T + P["patch_b"] + P["pos"][1:]
+    B = x.shape[0]
+    head = np.broadcast_to((P["cls"] + P["pos"][:1])[None], (B, 1, d))
+    tail = np.broadcast_to((latent_tokens + P["latent_pos"])[None], (B,) + latent_tokens.shape)
+    return np.concatenate([head, patches, tail], axis=1).astype(x.dtype), cols
+
+
+def _rab_stack_fwd(h, blocks, n_heads):
+    caches = []
+    h = np.transpose(h, (1, 0, 2))                 # the reference runs the blocks in LND (blocks.py:270)
+    for bp in blocks:
+        h, c = residual_attention_block_fwd(h, bp, n_heads)
+        caches.append(c)
+    return np.transpose(h, (1, 0, 2)), caches
+
+
+def _rab_stack_bwd(dh, caches):
+    dh = np.transpose(dh, (1, 0, 2))
+    grads = []
+    for c in reversed(caches):
+        dh, g = residual_attention_block_bwd(dh, c)
+        grads.append(g)
+    return np.transpose(dh, (1, 0, 2)), grads[::-1]
+
+
+def blocks_titok_encoder_fwd(x, latent_tokens, P, n_heads):
+    """blocks.TiTokEncoder.forward (blocks.py:254-282) -> z [B, token_size, 1, L]."""
+    tokens, cols = blocks_tokens_encoder(x, latent_tokens, P)
+    G, L = P["pos"].shape[0] - 1, latent_tokens.shape[0]
+    h0, c_pre = layer_norm_fwd(tokens, P["ln_pre_w"], P["ln_pre_b"])
+    h, c_blocks = _rab_stack_fwd(h0, P["blocks"], n_heads)
+    lat, c_post = layer_norm_fwd(h[:, 1 + G:], P["ln_post_w"], P["ln_post_b"])
+    ts = P["conv_out_w"].shape[0]
+    y = lat @ P["conv_out_w"].reshape(ts, -1).T + P["conv_out_b"]          # 1x1 conv over [B, d, L, 1]
+    z = np.transpose(y, (0, 2, 1))[:, :, None, :]
+    return z, (cols, c_pre, c_blocks, c_post, lat, h.shape, G, L, P)
+
+
+def blocks_titok_encoder_bwd(dz, cache):
+    """Gradients of blocks.TiTokEncoder wrt its parameters and latent_tokens (the image is a leaf)."""
+    cols, c_pre, c_blocks, c_post, lat, hshape, G, L, P = cache
+    d = hshape[-1]
+    ts = P["conv_out_w"].shape[0]
+    dy = np.transpose(dz[:, :, 0, :], (0, 2, 1))                            # [B, L, ts]
+    g = {"conv_out_w": (dy.reshape(-1, ts).T @ lat.reshape(-1, d)).reshape(P["conv_out_w"].shape), "conv_out_b": dy.reshape(-1, ts).sum(0)}
+    dlat = dy @ P["conv_out_w"].reshape(ts, d)
+    dl, g["ln_post_w"], g["ln_post_b"] = layer_norm_bwd(dlat, c_post)
+    dh = np.zeros(hshape, dtype=dz.dtype)
+    dh[:, 1 + G:] = dl
+    dh0, g["blocks"] = _rab_stack_bwd(dh, c_blocks)
+    dtok, g["ln_pre_w"], g["ln_pre_b"] = layer_norm_bwd(dh0, c_pre)
+    dsum = dtok.sum(axis=0)                                                 # [T, d]
+    g["cls"] = dsum[:1]
+    g["pos"] = dsum[:1 + G]
+    g["latent_pos"] = dsum[1 + G:]
+    g["latent_tokens"] = dsum[1 + G:]
+    dpe = dtok[:, 1:1 + G].reshape(-1, d)
+    g["patch_b"] = dpe.sum(axis=0)
+    g["patch_w"] = (dpe.T @ cols.reshape(-1, cols.shape[-1])).reshape(P["patch_w"].shape)
+    return g
+
+
+def blocks_titok_decoder_fwd(zq, P, n_heads, grid, p):
+    """blocks.TiTokDecoder.forward up to (not including) the final 3x3 conv_out (blocks.py:337-360): zq [B, ts, 1, L] ->
+    image [B, 3, grid p, grid p]."""
+    B, ts, _, L = zq.shape
+    d = P["embed_w"].shape[0]
+    x = np.transpose(zq.reshape(B, ts, L), (0, 2, 1)) @ P["embed_w"].T + P["embed_b"] + P["latent_pos"][:L]
+    G = grid * grid
+    head = np.concatenate([P["cls"], np.broadcast_to(P["mask"].reshape(1, d), (G, d))], axis=0) + P["pos"]
+    tokens = np.concatenate([np.broadcast_to(head[None], (B, 1 + G, d)), x], axis=1).astype(zq.dtype)
+    h0, _ = layer_norm_fwd(tokens, P["ln_pre_w"], P["ln_pre_b"])
+    h, _ = _rab_stack_fwd(h0, P["blocks"], n_heads)
+    grid_tokens, _ = layer_norm_fwd(h[:, 1:1 + G], P["ln_post_w"], P["ln_post_b"])
+    img, _ = depatchify_fwd(grid_tokens, P["ffn_w"], P["ffn_b"], grid, grid, p)
+    return img, tokens
+
+
+def affine_fold(W, b, gamma, beta):
+    """csrc/affine_fold.cu: Linear(gamma * xhat + beta) == xhat @ (W diag(gamma))^T + (b + W beta)."""
+    return W * gamma[None, :], (0.0 if b is None else b) + W @ beta
+
+
+def affine_unfold_grads(dWf, dbf, W, gamma, beta):
+    """Gradients of (W, gamma, beta) from the gradients of the folded pair (dWf = d/dW', dbf = d/db')."""
+    return dWf * gamma[None, :] + np.outer(dbf, beta), (dWf * W).sum(axis=0), W.T @ dbf
+
+
+# ------------------------------------------------------------------------------------------------
 # Patch embedding as used by ViT (train_vit.py:34-36,38-45): Conv2d(k = s = p) == im2col GEMM,
 # flatten (h w) row-major, + pos_emb, prepend extra_emb (extra tokens FIRST, no pos-emb on them)
 # ------------------------------------------------------------------------------------------------

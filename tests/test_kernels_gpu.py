@@ -261,11 +261,13 @@ def test_flash_attention(ops, B, N, H, causal):
     _attn_case(ops, B, N, H, causal, seed=N + H)
 
 
-@pytest.mark.parametrize("N,spikes", [(197, (150,)), (197, (40, 100, 196)), (65, (64,)), (130, (33, 129))])
+@pytest.mark.parametrize("N,spikes", [(197, (150,)), (197, (40, 100, 196)), (65, (64,)), (130, (33, 129)),
+                                      (288, (100, 200, 287)), (320, (40, 170, 300)), (600, (33, 290, 599))])
 def test_flash_attention_lazy_rescale(ops, N, spikes):
     """The short-sequence forward exponentiates against the maximum of the FIRST 32-key chunk and only rescales when a
     later key beats it by more than 2^8: keys with very large norms outside the first chunk force that path (and rows
-    whose scores towards them are negative must be unaffected)."""
+    whose scores towards them are negative must be unaffected).  N > 256: the streaming forward takes the first chunk of
+    every 128-key block as the block's reference and redoes a block exactly (two passes) when a later chunk exceeds it."""
     B, H = 2, 2
     rng = np.random.default_rng(N + len(spikes))
     d = H * 64

@@ -498,3 +498,58 @@ def test_videogpt_generate_edge_shapes(golden_dir, B, T0, n):
     assert torch.equal(out[sure, T0], lg.argmax(-1)[sure])
     with pytest.raises(ValueError):
         model.generate(prompt, 32 - T0 + 1)               # would exceed max_tokens = 32 positions
+
+
+def test_blocks_titok_encoder_decoder_match_reference_golden(golden_dir):
+    """blocks.TiTokEncoder / TiTokDecoder drop-ins (fused token-sequence assembly, LayerNorm-folded ResidualAttentionBlock
+    stack) against tests/golden/blocks_titok.npz, generated by the reference's own classes on CPU fp32 (make_golden.py
+    blocks_titok): outputs, the gradients of latent_tokens / z, every small parameter gradient in full, and norm + first 32
+    values of every parameter gradient."""
+    from b200vit import modules as M
+    from tests.test_oracle_golden import blocks_titok_weights
+    g = np.load(os.path.join(golden_dir, "blocks_titok.npz"))
+
+    class Cfg:
+        image_size, patch_size, transformer, latent_tokens, latent_dim = 64, 16, "small", 8, 12
+
+    def load(model, tag):
+        w = blocks_titok_weights(g, tag)
+        assert list(model.state_dict().keys()) == list(w.keys()), "state_dict keys/order must equal the reference's"
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()})
+        return model.to(DEV)
+
+    def check_all(model, tag):
+        grads = dict(model.named_parameters())
+        for name, norm, head in zip(g[f"{tag}_grad_names"], g[f"{tag}_grad_norms"], g[f"{tag}_grad_heads"]):
+            got = grads[str(name)].grad
+            assert got is not None, name
+            got = got.float().cpu().numpy()
+            assert abs(np.linalg.norm(got.astype(np.float64)) - norm) < 3e-2 * norm + 1e-7, name
+            if got.size >= 32 and np.linalg.norm(head) > 0.3 * norm * np.sqrt(32 / got.size):
+                # 32 individual elements of a gradient summed over only 50 token rows: element-wise bf16 noise is a few per
+                # cent of the typical magnitude, so the sample is compared as a vector (direction + size), not per element
+                assert rel_l2(got.reshape(-1)[:32], head) < 1e-1 and cosine(got.reshape(-1)[:32], head) > 0.995, name
+            key = f"{tag}_g_{name}"
+            if key in g.files:
+                check_grad(grads[str(name)].grad, g[key], str(name), tol=3e-2)
+
+    enc = load(M.BlocksTiTokEncoder(Cfg()), "enc")
+    x = torch.from_numpy(g["enc_x"]).to(DEV)
+    lt = torch.from_numpy(g["enc_latent_tokens"]).to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        z = enc(x, lt)
+    assert z.shape == (2, 12, 1, 8) and z.dtype == torch.float32
+    assert rel_l2(z.detach().cpu().numpy(), g["enc_z"]) < 2e-2
+    z.backward(torch.from_numpy(g["enc_dz"]).to(DEV))
+    check_grad(lt.grad, g["enc_dlatent_tokens"], "d latent_tokens", tol=3e-2)
+    check_all(enc, "enc")
+
+    dec = load(M.BlocksTiTokDecoder(Cfg()), "dec")
+    zq = torch.from_numpy(g["dec_zq"]).to(DEV).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        img = dec(zq)
+    assert img.shape == (2, 3, 64, 64)
+    assert rel_l2(img.detach().float().cpu().numpy(), g["dec_img"]) < 2e-2
+    img.float().backward(torch.from_numpy(g["dec_dimg"]).to(DEV))
+    check_grad(zq.grad, g["dec_dzq"], "d z_quantized", tol=3e-2)
+    check_all(dec, "dec")

@@ -321,3 +321,86 @@ def test_videogpt_oracle(golden_dir):
                 break
             assert toks[b, 5 + j] == ref[b, 5 + j], (b, j)
             assert abs(margins[b, j] - ref_m[b, j]) < 2e-2 * max(1.0, ref_m[b, j])
+
+
+# ------------------------------------------------------------------------------------------------ blocks.py encoder / decoder
+def blocks_titok_weights(g, tag):
+    """The weights tests/golden/make_golden.py:gen_blocks_titok gave the reference blocks.TiTokEncoder / TiTokDecoder
+    (det_weights recipe: numpy Generator in state_dict order, scale 0.03, LayerNorm weights recentred at 1)."""
+    rng = np.random.default_rng({"enc": 71, "dec": 72}[tag])
+    w = {}
+    for k, shp in zip(g[f"{tag}_keys"], g[f"{tag}_shapes"]):
+        k = str(k)
+        shape = tuple(int(v) for v in str(shp).split(",")) if str(shp) else ()
+        a = rng.standard_normal(shape).astype(np.float32) * 0.03
+        if k.endswith("ln_1.weight") or k.endswith("ln_2.weight") or k in ("ln_pre.weight", "ln_post.weight"):
+            a = a + 1.0
+        w[k] = a
+    return w
+
+
+def _blocks_P(w, n_layers):
+    P = {"cls": w["class_embedding"], "pos": w["positional_embedding"], "latent_pos": w["latent_token_positional_embedding"],
+         "ln_pre_w": w["ln_pre.weight"], "ln_pre_b": w["ln_pre.bias"], "ln_post_w": w["ln_post.weight"], "ln_post_b": w["ln_post.bias"]}
+    P["blocks"] = [{"ln1_w": w[f"transformer.{i}.ln_1.weight"], "ln1_b": w[f"transformer.{i}.ln_1.bias"],
+                    "in_w": w[f"transformer.{i}.attn.in_proj_weight"], "in_b": w[f"transformer.{i}.attn.in_proj_bias"],
+                    "out_w": w[f"transformer.{i}.attn.out_proj.weight"], "out_b": w[f"transformer.{i}.attn.out_proj.bias"],
+                    "ln2_w": w[f"transformer.{i}.ln_2.weight"], "ln2_b": w[f"transformer.{i}.ln_2.bias"],
+                    "fc_w": w[f"transformer.{i}.mlp.c_fc.weight"], "fc_b": w[f"transformer.{i}.mlp.c_fc.bias"],
+                    "proj_w": w[f"transformer.{i}.mlp.c_proj.weight"], "proj_b": w[f"transformer.{i}.mlp.c_proj.bias"]}
+                   for i in range(n_layers)]
+    return P
+
+
+def test_blocks_titok_encoder_decoder_oracle(golden_dir):
+    """oracle blocks_titok_encoder_fwd / _bwd and blocks_titok_decoder_fwd against the reference's own blocks.TiTokEncoder /
+    TiTokDecoder (tests/golden/blocks_titok.npz, make_golden.py blocks_titok): the token-sequence assembly (class / mask
+    tokens, both positional tables, latent tokens), ln_pre, 8 ResidualAttentionBlocks, ln_post, conv_out / ffn."""
+    g = _load(golden_dir, "blocks_titok.npz")
+    w = blocks_titok_weights(g, "enc")
+    P = _blocks_P(w, 8)
+    P.update(patch_w=w["patch_embed.weight"], patch_b=w["patch_embed.bias"], conv_out_w=w["conv_out.weight"], conv_out_b=w["conv_out.bias"])
+    z, cache = O.blocks_titok_encoder_fwd(g["enc_x"].astype(np.float64), g["enc_latent_tokens"].astype(np.float64),
+                                          {k: (v.astype(np.float64) if isinstance(v, np.ndarray) else [{a: b.astype(np.float64) for a, b in d.items()} for d in v])
+                                           for k, v in P.items()}, 8)
+    _close(z, g["enc_z"], rtol=1e-3, atol=1e-4)
+    gr = O.blocks_titok_encoder_bwd(g["enc_dz"].astype(np.float64), cache)
+    _close(gr["latent_tokens"], g["enc_dlatent_tokens"], rtol=2e-3, atol=2e-4)
+    for name, key in (("class_embedding", "cls"), ("positional_embedding", "pos"), ("latent_token_positional_embedding", "latent_pos"),
+                      ("ln_pre.weight", "ln_pre_w"), ("ln_pre.bias", "ln_pre_b"), ("ln_post.weight", "ln_post_w"),
+                      ("ln_post.bias", "ln_post_b"), ("conv_out.bias", "conv_out_b"), ("patch_embed.bias", "patch_b")):
+        _close(gr[key].reshape(g[f"enc_g_{name}"].shape), g[f"enc_g_{name}"], rtol=2e-3, atol=2e-4)
+    norms = dict(zip((str(n) for n in g["enc_grad_names"]), g["enc_grad_norms"]))
+    assert abs(np.linalg.norm(gr["patch_w"]) - norms["patch_embed.weight"]) < 2e-3 * norms["patch_embed.weight"]
+    for i in (0, 7):
+        for ours, theirs in (("ln1_w", "ln_1.weight"), ("in_w", "attn.in_proj_weight"), ("fc_w", "mlp.c_fc.weight"), ("proj_b", "mlp.c_proj.bias")):
+            n = norms[f"transformer.{i}.{theirs}"]
+            assert abs(np.linalg.norm(gr["blocks"][i][ours]) - n) < 2e-3 * n, (i, ours)
+    # decoder (up to the 3x3 conv_out, which is outside the path)
+    w = blocks_titok_weights(g, "dec")
+    P = _blocks_P(w, 8)
+    P.update(embed_w=w["decoder_embed.weight"], embed_b=w["decoder_embed.bias"], mask=w["mask_token"], ffn_w=w["ffn.0.weight"], ffn_b=w["ffn.0.bias"])
+    img, _ = O.blocks_titok_decoder_fwd(g["dec_zq"], P, 8, 4, 16)
+    _close(img, g["dec_img_before_conv_out"], rtol=2e-3, atol=2e-4)
+
+
+def test_affine_fold_identity():
+    """The algebra behind csrc/affine_fold.cu, in fp64: folding an affine LayerNorm into the next Linear changes neither the
+    output nor (after unfolding) any gradient."""
+    rng = np.random.default_rng(3)
+    M, K, N = 37, 24, 40
+    x = rng.standard_normal((M, K)); W = rng.standard_normal((N, K)); b = rng.standard_normal(N)
+    gamma = 1 + 0.3 * rng.standard_normal(K); beta = 0.2 * rng.standard_normal(K); dy = rng.standard_normal((M, N))
+    a, c = O.layer_norm_fwd(x, gamma, beta)
+    y = O.linear_fwd(a, W, b)
+    xhat, _ = O.layer_norm_fwd(x)
+    Wf, bf = O.affine_fold(W, b, gamma, beta)
+    np.testing.assert_allclose(O.linear_fwd(xhat, Wf, bf), y, rtol=1e-12, atol=1e-12)
+    da, dW, db = O.linear_bwd(dy, a, W)
+    _, dgamma, dbeta = O.layer_norm_bwd(da, c)
+    _, dWf, dbf = O.linear_bwd(dy, xhat, Wf)
+    dW2, dgamma2, dbeta2 = O.affine_unfold_grads(dWf, dbf, W, gamma, beta)
+    np.testing.assert_allclose(dW2, dW, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(dgamma2, dgamma, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(dbeta2, dbeta, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(dbf, db, rtol=1e-12)

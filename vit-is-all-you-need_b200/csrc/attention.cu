@@ -245,38 +245,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       mbar_wait(s_full, j & 1, 31);
       tc_fence_after();
       const bool need_mask = ((j + 1) * AT_BK > p.N) || (CAUSAL && (j + 1) * AT_BK > q0 + 1);
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_ld_wait();
-        if (need_mask) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int key = j * AT_BK + c * 32 + i;
-            const bool ok = key < p.N && (!CAUSAL || key <= q);
-            mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-      }
-      float m_new = fmaxf(m, mx * p.scale_log2e);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2_approx(m - m_use);
-      l *= alpha;
-#pragma unroll
-      for (int i = 0; i < AT_HD; ++i) oacc[i] *= alpha;
-      // pass 2: probabilities -> bf16 operand tile
-      float rowsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_ld_wait();
+      auto masked_score = [&](uint32_t bits, int key) -> float {
+        const bool ok = key < p.N && (!CAUSAL || key <= q);
+        return ok ? __uint_as_float(bits) : -INFINITY;
+      };
+      // probabilities of one 32-key chunk against the reference m_use -> bf16 operand chunk in shared memory
+      auto exp_chunk = [&](const uint32_t (&v)[32], int c, float m_use, float& rowsum) {
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -297,7 +271,65 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           w[i >> 1] = pack_bf16(p0, p1);
         }
         store_operand_chunk(smem + FwdSmem::P, r, c, w);
+      };
+      auto chunk_max = [&](const uint32_t (&v)[32], int c) -> float {
+        float mx = -INFINITY;
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, masked_score(v[i], j * AT_BK + c * 32 + i));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        return mx * p.scale_log2e;
+      };
+      // ONE pass over S (round 2; the kernel is bound by the TMEM read port, 64 B/clk/SM, and the separate row-maximum
+      // pass read every score twice): the reference of this key block is max(running reference, maximum of the block's
+      // FIRST 32-key chunk); later chunks are exponentiated against it as long as no row of the warp exceeds it by more
+      // than 2^TAU (P <= 256 then, and O / l does not depend on the reference).  S is NOT overwritten here (P goes to
+      // shared memory), so in the rare other case the block is simply redone with the exact two-pass scheme below.
+      constexpr float TAU = 8.0f;
+      float m_new = m, m_use = 0.f, alpha = 1.f, rowsum = 0.f;
+      bool redo = false;
+      {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off, v);
+        tmem_ld_wait();
+        m_new = fmaxf(m, chunk_max(v, 0));
+        m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        exp_chunk(v, 0, m_use, rowsum);
+#pragma unroll 1
+        for (int c = 1; c < nch; ++c) {
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld_wait();
+          if (__any_sync(0xffffffffu, chunk_max(v, c) > m_use + TAU)) { redo = true; break; }
+          exp_chunk(v, c, m_use, rowsum);
+        }
       }
+      if (redo) {   // exact two-pass softmax of this block (warp-uniform branch)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld_wait();
+          mx = fmaxf(mx, chunk_max(v, c));
+        }
+        m_new = fmaxf(m, mx);
+        m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        rowsum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < nch; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld_wait();
+          exp_chunk(v, c, m_use, rowsum);
+        }
+      }
+      alpha = ex2_approx(m - m_use);
+      l *= alpha;
+#pragma unroll
+      for (int i = 0; i < AT_HD; ++i) oacc[i] *= alpha;
       l += rowsum;
       m = m_new;
       fence_proxy_async_smem();
