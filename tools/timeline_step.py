@@ -26,6 +26,8 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--model", type=str, default="B")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--dropout", type=float, default=0.0)
+ap.add_argument("--bucket-mb", type=float, default=0.0, help="torchrun only: gradient bucket size; 0 = one bucket reduced after backward (bench.py default)")
+ap.add_argument("--grad-compress", type=str, default="bf16", choices=["none", "bf16"])
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -40,7 +42,7 @@ if world > 1:  # torchrun: the same step through the data-parallel wrapper (rank
     from b200vit import ddp
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
-    net = ddp.DataParallel(model)
+    net = ddp.DataParallel(model, bucket_mb=args.bucket_mb if args.bucket_mb > 0 else 1e9, compress_bf16=(args.grad_compress == "bf16"))
 from b200vit.optim import AdamW  # noqa: E402
 optim = AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2)
 x = torch.randn(args.batch, 3, 224, 224, device=dev)
@@ -100,7 +102,22 @@ for s, e, n in evs:
     agg[short][1] += 1
 k = args.steps
 span = t_last - t_first
-print(f"# in-step kernel timeline: ViT-{args.model}/16 224 batch {args.batch}, {k} steps under torch.profiler (CUPTI)\n")
+print(f"# in-step kernel timeline: ViT-{args.model}/16 224 batch {args.batch}, {k} steps under torch.profiler (CUPTI)"
+      + (f", rank 0 of {world} GPUs, gradient exchange: " + ("one bucket after backward" if args.bucket_mb <= 0 else f"{args.bucket_mb:g} MB buckets overlapped")
+         + f", {args.grad_compress}" if world > 1 else "") + "\n")
+if world > 1:
+    nccl = [(s_, e_, n_) for s_, e_, n_ in evs if "nccl" in n_.lower()]
+    adam = [(s_, e_) for s_, e_, n_ in evs if "adamw_kernel" in n_]
+    if nccl and adam:
+        per = len(nccl) // k
+        print(f"* NCCL kernels per step: {per}; total {sum(e_ - s_ for s_, e_, _ in nccl) / k:.0f} us/step; names: "
+              + ", ".join(sorted({re.sub(r'[(<].*', '', n_) for _, _, n_ in nccl})))
+        # exposed tail: from the end of the last non-NCCL kernel before each AdamW launch to the AdamW launch
+        tails = []
+        for a_s, _ in adam:
+            prev = max((e_ for s_, e_, n_ in evs if e_ <= a_s and "nccl" not in n_.lower() and "adamw" not in n_), default=a_s)
+            tails.append(a_s - prev)
+        print(f"* compute idle before AdamW (waiting for the last all-reduce): {sum(tails) / len(tails):.0f} us/step")
 print(f"* un-profiled step time (CUDA events): {plain_ms:.2f} ms")
 print(f"* profiled span per step: {span / k / 1e3:.2f} ms; GPU busy per step: {busy / k / 1e3:.2f} ms; "
       f"idle (gaps between kernels) per step: {(span - busy) / k / 1e3:.2f} ms over {len(gaps) / k:.0f} gaps")

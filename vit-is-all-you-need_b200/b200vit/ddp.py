@@ -47,6 +47,9 @@ class DataParallel(torch.nn.Module):
         super().__init__()
         import os
         self.compress_bf16 = (os.environ.get("B200VIT_DDP_BF16", "0") == "1") if compress_bf16 is None else bool(compress_bf16)
+        # diagnosis only (tools/ddp_ab2.sh): no collective at all, to separate the all-reduce's cost from rank-to-rank skew
+        self._skip_comm = os.environ.get("B200VIT_DDP_DIAG_SKIP_COMM", "0") == "1"
+        self._avg_op = os.environ.get("B200VIT_DDP_AVG", "0") == "1"
         self.module = module
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -177,7 +180,7 @@ class DataParallel(torch.nn.Module):
             self._launch(b)
 
     def _launch(self, b):
-        if self.world == 1:
+        if self.world == 1 or self._skip_comm:
             return
         if self.comm_stream is not None:
             ev = torch.cuda.Event()
@@ -189,8 +192,14 @@ class DataParallel(torch.nn.Module):
                     if b.flat16 is None:
                         b.flat16 = torch.empty(b.flat.numel(), device=b.flat.device, dtype=torch.bfloat16)
                     ops.cast_bf16(b.flat, out=b.flat16)
-                    dist.all_reduce(b.flat16, op=dist.ReduceOp.AVG, group=self.pg, async_op=True).wait()   # comm stream waits
-                    ops.cast_f32_from_bf16(b.flat16, b.flat)
+                    # SUM (not AVG): NCCL's in-switch NVLS reduction has no pre-multiplied average for bf16; the 1 / world
+                    # factor is applied for free by the cast back into the fp32 bucket
+                    if self._avg_op:      # A/B knob B200VIT_DDP_AVG=1: NCCL's own average (measured: RING_LL instead of NVLS)
+                        dist.all_reduce(b.flat16, op=dist.ReduceOp.AVG, group=self.pg, async_op=True).wait()
+                        ops.cast_f32_from_bf16(b.flat16, b.flat)
+                    else:
+                        dist.all_reduce(b.flat16, op=dist.ReduceOp.SUM, group=self.pg, async_op=True).wait()   # comm stream waits
+                        ops.cast_f32_from_bf16(b.flat16, b.flat, scale=1.0 / self.world)
                     b.done = torch.cuda.Event()
                     b.done.record(self.comm_stream)
                 else:
