@@ -89,6 +89,15 @@ gpt = train_videogpt.VideoGPT(train_videogpt.VideoGPTConfig(8, 32, "XS", 4, 0.0)
 out["videogpt"] = {k: list(v.shape) for k, v in gpt.state_dict().items()}
 vqgan = train_vit_vqgan.ViTVQGAN(train_vit_vqgan.ViTVQGANConfig(32, 4, 64, 12, "XS"))
 out["vqgan"] = {k: list(v.shape) for k, v in vqgan.state_dict().items()}
+import blocks
+class _BCfg:
+    image_size, patch_size, transformer, latent_tokens, latent_dim = 64, 16, "small", 8, 12
+benc, bdec = blocks.TiTokEncoder(_BCfg()), blocks.TiTokDecoder(_BCfg())
+out["blocks_enc"] = {k: list(v.shape) for k, v in benc.state_dict().items()}
+out["blocks_dec"] = {k: list(v.shape) for k, v in bdec.state_dict().items()}
+out["blocks_param_order"] = [n for n, _ in benc.named_parameters()] + [n for n, _ in bdec.named_parameters()]
+out["blocks_classes"] = [type(benc).__module__, type(bdec).__module__, type(benc.transformer[0]).__module__,
+                         blocks.VectorQuantizer.__module__, blocks.TATiTokDecoder.__module__]
 out["classes"] = [type(titok.enc.vit).__module__, type(titok.quant).__module__, type(vit.vit.transformer).__module__,
                   type(titok.enc).__module__, type(titok.dec).__module__, type(gpt).__module__, type(vqgan.encoder).__module__,
                   type(vqgan.decoder).__module__]
@@ -110,6 +119,12 @@ def test_launcher_swaps_classes_and_keeps_state_dict_contract():
     assert ours["vqgan"] == ref["vqgan"], "ViTVQGAN (train_vit_vqgan.py) state_dict keys/shapes must equal the reference's"
     assert all(c.startswith("b200vit") for c in ours["classes"]), ours["classes"]
     assert not any(c.startswith("b200vit") for c in ref["classes"])
+    # blocks.py: TiTokEncoder / TiTokDecoder / ResidualAttentionBlock / VectorQuantizer are the drop-ins, TATiTokDecoder (out of
+    # scope) is still the reference's own class, and keys / shapes / parameter order are the reference's
+    assert ours["blocks_enc"] == ref["blocks_enc"] and ours["blocks_dec"] == ref["blocks_dec"]
+    assert ours["blocks_param_order"] == ref["blocks_param_order"]
+    assert all(c.startswith("b200vit") for c in ours["blocks_classes"][:4]), ours["blocks_classes"]
+    assert not ours["blocks_classes"][4].startswith("b200vit")
 
 
 @pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")

@@ -4,7 +4,8 @@ Public surface mirrors the reference (SnakeOnex/vit-is-all-you-need): see module
 ../shim/ (transformer.py, blocks.py, train_vit.py) let the reference's training scripts import these classes
 by their original bare module names.
 """
-from .modules import (Attention, B, CrossEntropyLoss, L, PatchConv2d, Quantizer, ResidualAttentionBlock, S, Transformer, TransformerConfig,  # noqa: F401
+from .modules import (Attention, B, BlocksTiTokDecoder, BlocksTiTokEncoder, CrossEntropyLoss, L, PatchConv2d, Quantizer, ResidualAttentionBlock, S,  # noqa: F401
+                      Transformer, TransformerConfig,
                       TiTok, TiTokDecoder, TiTokEncoder, TransformerLayer, UViTBlock, VectorQuantizer, VideoGPT, ViT, ViTClassifier, ViTConfig, transformer_configs)
 
 __version__ = "0.1.0"

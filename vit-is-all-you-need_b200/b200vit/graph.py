@@ -46,9 +46,8 @@ class GraphedTrainStep:
         self._captured_grads = [p.grad for p in model.parameters()]
 
     def _invalidate_weight_cache(self):
-        for p in self.model.parameters():
-            if hasattr(p, "_b200_bf16"):
-                del p._b200_bf16
+        from . import functional as Fn
+        Fn.invalidate_weight_cache(self.model)   # bf16 operands, LayerNorm-folded operands, de-patchify operands
 
     def _eager_step(self, zero=True):
         if zero:
