@@ -268,10 +268,15 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
+        # the SAME workload identity as the GPU arm (its config keys), timed as a bounded sample on the host cores
         "config": {"workload": "ViT-B/16 224px ImageNet-shape train step (fwd + CE + bwd + AdamW), configs[1]",
-                   "arm": ("the reference's own CPU path (unmodified modules from baseline/_ref)" if kind == "reference"
-                           else "numpy oracle port of the reference (baseline/_ref absent)"),
-                   "sample_batch": batch, "parallelism": "cpu"},
+                   "per_gpu_batch": args.batch, "global_batch": args.batch * max(args.gpus, 1), "seq_len": NTOK,
+                   "parallelism": f"dp{max(args.gpus, 1)}", "dropout": 0.0,
+                   "optimizer": "torch.optim.AdamW" if kind == "reference" else "numpy AdamW oracle",
+                   "train_gflop_per_image": train_flops_per_image() / 1e9},
+        "reference_arm": {"what": ("the reference's own CPU path (unmodified modules from baseline/_ref)" if kind == "reference"
+                                   else "numpy oracle port of the reference (baseline/_ref absent)"),
+                          "sample_batch": batch, "runs_on": "host cores of rank 0"},
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
