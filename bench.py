@@ -41,11 +41,12 @@ def train_flops_per_image():
 def load_gemm_traffic():
     """Per-launch DRAM bytes (read + write) of the tcgen05 GEMM family from the committed `ncu --set full` capture
     (profiles/r1_gemm_traffic.json, written by tools/ncu_step_summary.py); None when no capture is committed."""
-    path = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
-    try:
-        return float(json.load(open(path))["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):   # the newest committed capture
+        try:
+            return float(json.load(open(os.path.join(ROOT, "profiles", name)))["dram_bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def load_peaks():

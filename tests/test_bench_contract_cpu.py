@@ -42,3 +42,21 @@ def test_train_flops_formula():
     assert abs(bench.train_flops_per_image() / 1e9 - 96.786) < 0.01
     t = bench.load_gemm_traffic()
     assert t is None or t > 1e6
+
+
+def test_workload_flop_formulas_and_descriptors():
+    """bench_workloads: the algorithmic work per unit follows SURVEY.md §8(d) (ViT-L/16: 339.274 GFLOP per trained image) and every
+    workload name the parser accepts has a descriptor (no GPU needed: descriptors are built lazily, models are not)."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "vit-is-all-you-need_b200"))
+    import torch
+
+    import bench_workloads as W
+    from b200vit import modules as M
+    w = W._workload("vit_l", torch, M, None)
+    assert abs(w["flops_per_unit"] / 1e9 - 339.274) < 0.01 and w["batch"] == 256 and w["reference"] is None
+    for name in ("vit_ti", "titok_s", "tatitok_s", "videogpt_b"):
+        d = W._workload(name, torch, M, None)
+        assert d["flops_per_unit"] > 0 and d["unit"] and d["metric"] and callable(d["ours"]) and callable(d["inputs"])
+    x = W._workload("videogpt_b", torch, M, None)["inputs"](2, torch.Generator().manual_seed(0))
+    assert x[0].shape == (2, 16, 64) and x[0].dtype == torch.int64
