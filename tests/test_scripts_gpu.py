@@ -77,13 +77,18 @@ def test_train_vit_script_unchanged(tmp_path):
     model.load_state_dict(sd, strict=True)
 
 
-def test_train_titok_script_unchanged(tmp_path):
+@pytest.mark.parametrize("script", ["train_titok.py", "train_vit_vqgan.py"])
+def test_train_titok_script_unchanged(tmp_path, script):
+    """train_titok.py (TiTok: 16 latent tokens) and its all-tokens twin train_vit_vqgan.py (ViT-VQGAN: one latent per patch, L1
+    reconstruction loss, train_vit_vqgan.py:150-157): same harness, same comparison."""
     os.makedirs(tmp_path / "titok_models", exist_ok=True)      # train_titok.py:172 saves there without creating it
-    args = ["--image_size", "64", "--patch_size", "8", "--latent_tokens", "16", "--codebook_size", "512", "--latent_dim", "12",
+    args = ["--image_size", "64", "--patch_size", "8", "--codebook_size", "512", "--latent_dim", "12",
             "--transformer", "S", "--bs", "8", "--epochs", "5", "--warmup_steps", "2", "--lr", "1e-4"]
-    ours, out_o = _run("train_titok.py", args, str(tmp_path), False, 16)
-    plain, out_p = _run("train_titok.py", args, str(tmp_path), True, 16)
-    _save("train_titok", plain, ours)
+    if script == "train_titok.py":
+        args += ["--latent_tokens", "16"]
+    ours, out_o = _run(script, args, str(tmp_path), False, 16)
+    plain, out_p = _run(script, args, str(tmp_path), True, 16)
+    _save(script[:-3], plain, ours)
     assert "STATS: enc_params=" in out_o
     for key in ("train/loss", "train/l1_loss", "train/quant_loss"):
         _check(key, plain, ours)
