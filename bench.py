@@ -493,9 +493,11 @@ def main():
                          "(profiles/r2_ddp_8gpu_ab.md): overlapped 32 MB buckets 31.98 ms/step, one deferred bucket 30.99 (fp32) / "
                          "30.73 (bf16): NCCL's CTAs cannot share an SM with the persistent GEMM CTAs (the GEMM owns the whole register "
                          "file), so every overlapped bucket displaces GEMM CTAs of a statically partitioned grid")
-    ap.add_argument("--grad-compress", type=str, default="bf16", choices=["none", "bf16"],
-                    help="bf16: the bucket crosses NVLink as bf16 (cast - all-reduce(avg) - cast back into the fp32 bucket), like "
-                         "torch's bf16_compress_hook; none: fp32 all-reduce")
+    ap.add_argument("--grad-compress", type=str, default="none", choices=["none", "bf16"],
+                    help="none (default): fp32 all-reduce of the fp32 gradient bucket; bf16: the bucket crosses NVLink as bf16 (cast - "
+                         "all-reduce(sum) - cast back with 1/world into the fp32 bucket), like torch's bf16_compress_hook -- measured "
+                         "0.27 ms/step faster at 8 GPUs (30.73 vs 30.99 ms), gradients differ by 2.5e-3 rel-L2; not the default so that the "
+                         "headline scaling numbers carry no reduced-precision step")
     ap.add_argument("--impl", type=str, default="b200vit", choices=["b200vit", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=16, help="batch of the bounded CPU-baseline sample (a few seconds per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -27,7 +27,7 @@ ap.add_argument("--model", type=str, default="B")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--dropout", type=float, default=0.0)
 ap.add_argument("--bucket-mb", type=float, default=0.0, help="torchrun only: gradient bucket size; 0 = one bucket reduced after backward (bench.py default)")
-ap.add_argument("--grad-compress", type=str, default="bf16", choices=["none", "bf16"])
+ap.add_argument("--grad-compress", type=str, default="none", choices=["none", "bf16"])
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
